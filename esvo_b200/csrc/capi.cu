@@ -1,0 +1,346 @@
+// esvo_b200 product code -- C ABI (include/esvo_b200.h) over the CUDA stages.
+// Host logic only: argument checks, buffer management, H2D/D2H staging and kernel sequencing.
+// There is no CPU fallback: every entry point that computes does so with the kernels in this
+// directory, and esvo_create fails when no CUDA device is usable.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace esvo {
+
+template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+// 5x5 Gaussian on u8 (cv::GaussianBlur sigma=0: [1 4 6 4 1]/16 per axis, fixed point, round half
+// up, BORDER_REFLECT_101) -- TimeSurfaceObservation::GaussianBlurTS / getTimeSurfaceNegative.
+__device__ __forceinline__ int refl101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+  return p;
+}
+__global__ void gauss5_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int W, int H, int pitch) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const int k[5] = {1, 4, 6, 4, 1};
+  int s = 0;
+#pragma unroll
+  for (int dy = -2; dy <= 2; ++dy) {
+    const uint8_t* row = src + (size_t)refl101(y + dy, H) * pitch;
+    int r = 0;
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) r += k[dx + 2] * row[refl101(x + dx, W)];
+    s += k[dy + 2] * r;
+  }
+  dst[(size_t)y * pitch + x] = (uint8_t)((s + 128) >> 8);
+}
+
+int smooth_obs(Ctx* c) {
+  dim3 b(32, 8), g(div_up(c->dc.W, 32), div_up(c->dc.H, 8));
+  gauss5_u8_kernel<<<g, b, 0, c->stream>>>(c->obs_l, c->obs_ls, c->dc.W, c->dc.H, c->dc.pitch);
+  gauss5_u8_kernel<<<g, b, 0, c->stream>>>(c->obs_r, c->obs_rs, c->dc.W, c->dc.H, c->dc.pitch);
+  c->launches += 2;
+  return ESVO_OK;
+}
+
+int map_alloc_inputs(Ctx* c, size_t n_ev, size_t n_poses) {
+  if (n_ev > c->ev_cap) {
+    size_t cap = std::max<size_t>(n_ev, 1024);
+    void* olds[] = {c->d_ex, c->d_ey, c->d_et, c->bm.flag, c->bm.disp, c->bm.pose_idx, c->bm.cost, c->bm.xrect,
+                    c->d_seeds, c->lm_flag, c->lm_res, c->d_pts};
+    for (void* p : olds) if (p) cudaFree(p);
+    ESVO_CUDA_TRY(c, dmalloc(&c->d_ex, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_ey, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_et, cap));
+    ESVO_CUDA_TRY(c, dmalloc(&c->bm.flag, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->bm.disp, cap));
+    ESVO_CUDA_TRY(c, dmalloc(&c->bm.pose_idx, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->bm.cost, cap));
+    ESVO_CUDA_TRY(c, dmalloc(&c->bm.xrect, 2 * cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_seeds, cap));
+    ESVO_CUDA_TRY(c, dmalloc(&c->lm_flag, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->lm_res, 3 * cap));
+    ESVO_CUDA_TRY(c, dmalloc(&c->d_pts, cap));
+    c->ev_cap = cap;
+  }
+  if (n_poses > c->pose_cap) {
+    size_t cap = std::max<size_t>(n_poses, 256);
+    if (c->d_pose_t) cudaFree(c->d_pose_t);
+    if (c->d_poses) cudaFree(c->d_poses);
+    ESVO_CUDA_TRY(c, dmalloc(&c->d_pose_t, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_poses, 16 * cap));
+    c->pose_cap = cap;
+  }
+  return ESVO_OK;
+}
+
+static int upload_tables(Ctx* c) {
+  const size_t npix = (size_t)c->dc.W * c->dc.H;
+  ESVO_CUDA_TRY(c, cudaMemcpy(c->d_lut, c->cam[0].lut.data(), 2 * npix * 8, cudaMemcpyHostToDevice));
+  ESVO_CUDA_TRY(c, cudaMemcpy(c->d_mask, c->cam[0].mask.data(), npix, cudaMemcpyHostToDevice));
+  for (int cam = 0; cam < 2; ++cam) {
+    ESVO_CUDA_TRY(c, cudaMemcpy(c->ts[cam].map1, c->cam[cam].map1.data(), npix * 4, cudaMemcpyHostToDevice));
+    ESVO_CUDA_TRY(c, cudaMemcpy(c->ts[cam].map2, c->cam[cam].map2.data(), npix * 4, cudaMemcpyHostToDevice));
+  }
+  return ESVO_OK;
+}
+
+static void rigid_inverse(const double* T, double* I) {
+  for (int i = 0; i < 16; ++i) I[i] = 0;
+  I[15] = 1;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) I[i * 4 + j] = T[j * 4 + i];
+  for (int i = 0; i < 3; ++i) {
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += I[i * 4 + k] * T[k * 4 + 3];
+    I[i * 4 + 3] = -s;
+  }
+}
+
+static int stage_mapping(Ctx* c, const uint16_t* ex, const uint16_t* ey, const int64_t* et, size_t n,
+                         const int64_t* pt, const double* poses, size_t np) {
+  int rc = map_alloc_inputs(c, n, np);
+  if (rc) return rc;
+  c->n_ev = n; c->n_poses = np;
+  if (n) {
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ex, ex, n * 2, cudaMemcpyHostToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ey, ey, n * 2, cudaMemcpyHostToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_et, et, n * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (np) {
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_pose_t, pt, np * 8, cudaMemcpyHostToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_poses, poses, np * 16 * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  return ESVO_OK;
+}
+
+static int fetch_counters(Ctx* c) {
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->d_counters, kCounters * 8, cudaMemcpyDeviceToHost, c->stream));
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return ESVO_OK;
+}
+
+}  // namespace esvo
+
+using namespace esvo;
+
+#define CHECK_CTX(c) do { if (!(c)) return ESVO_ERR_INVALID_ARG; cudaSetDevice((c)->device); } while (0)
+
+extern "C" {
+
+ESVO_API void esvo_default_params(esvo_params* p) { host_default_params(p); }
+ESVO_API const char* esvo_version(void) { return "esvo_b200 0.1 (sm_100a)"; }
+ESVO_API const char* esvo_last_error(esvo_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+ESVO_API void* esvo_stream(esvo_ctx* c) { return c ? (void*)c->stream : nullptr; }
+ESVO_API uint64_t esvo_launch_count(esvo_ctx* c) { return c ? c->launches : 0; }
+ESVO_API int esvo_sync(esvo_ctx* c) { CHECK_CTX(c); ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return ESVO_OK; }
+
+ESVO_API esvo_ctx* esvo_create(int device, const esvo_calib* left, const esvo_calib* right, const esvo_params* p,
+                               int* status_out) {
+  auto fail = [&](int code) -> esvo_ctx* { if (status_out) *status_out = code; return nullptr; };
+  if (!left || !right || !p || left->width != right->width || left->height != right->height || left->width <= 0 ||
+      left->height <= 0)
+    return fail(ESVO_ERR_INVALID_ARG);
+  if (p->patch_size_x * p->patch_size_y > kMaxPatch || p->patch_size_x < 1 || p->patch_size_y < 1 ||
+      !(p->patch_size_x & 1) || !(p->patch_size_y & 1))
+    return fail(ESVO_ERR_UNSUPPORTED);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return fail(ESVO_ERR_NO_DEVICE);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(ESVO_ERR_NO_DEVICE);
+  esvo_ctx* c = new esvo_ctx();
+  c->device = device;
+  c->prm = *p;
+  host_camera_init(c->cam[0], *left);
+  host_camera_init(c->cam[1], *right);
+  DevConsts& d = c->dc;
+  d.W = left->width; d.H = left->height; d.pitch = (d.W + 15) / 16 * 16;
+  d.wx = p->patch_size_x; d.wy = p->patch_size_y;
+  d.baseline = host_baseline(c->cam[1]);
+  {  // esvo_Mapping.cpp:110-116
+    double f = (c->cam[0].P[0] + c->cam[0].P[5]) / 2, b = d.baseline;
+    size_t minD = std::max(size_t(std::floor(f * b * p->invdepth_min_range)), (size_t)0);
+    size_t maxD = size_t(std::ceil(f * b * p->invdepth_max_range));
+    d.dmin = (int)std::max(minD, (size_t)p->bm_min_disparity);
+    d.dmax = (int)std::min(maxD, (size_t)p->bm_max_disparity);
+  }
+  d.step = std::max(1, p->bm_step); d.updown = p->bm_updown; d.zncc_thr = p->bm_zncc_threshold;
+  d.fx = c->cam[0].P[0]; d.fy = c->cam[0].P[5]; d.cx = c->cam[0].P[2]; d.cy = c->cam[0].P[6];
+  std::memcpy(d.Pl, c->cam[0].P, sizeof(d.Pl)); std::memcpy(d.Pr, c->cam[1].P, sizeof(d.Pr));
+  d.lsnorm = p->lsnorm; d.max_iter = p->max_iteration; d.td_nu = p->td_nu; d.td_scale = p->td_scale;
+  d.td_scale2 = p->td_scale * p->td_scale;
+  d.td_stdvar = std::sqrt(p->td_nu / (p->td_nu - 2) * d.td_scale2);  // DepthProblem.h:34
+  d.NT = std::max(1, p->num_thread_mapping);
+  if (d.dmax >= d.dmin && (d.dmax - d.dmin) / d.step + 1 > 192 && d.step > 1) { delete c; return fail(ESVO_ERR_UNSUPPORTED); }
+  auto bail = [&](int code) -> esvo_ctx* { esvo_destroy(c); return fail(code); };
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ESVO_ERR_CUDA);
+  const size_t npix = (size_t)d.W * d.H, nimg = (size_t)d.pitch * d.H;
+  if (dmalloc(&c->d_lut, 2 * npix) || dmalloc(&c->d_mask, npix) || dmalloc(&c->obs_l, nimg) || dmalloc(&c->obs_r, nimg) ||
+      dmalloc(&c->obs_ls, nimg) || dmalloc(&c->obs_rs, nimg) || dmalloc(&c->d_T_left_world, 16) ||
+      dmalloc(&c->d_counters, kCounters) || cudaMallocHost((void**)&c->h_counters, kCounters * 8))
+    return bail(ESVO_ERR_CUDA);
+  cudaMemset(c->d_counters, 0, kCounters * 8);
+  cudaMemset(c->obs_l, 0, nimg); cudaMemset(c->obs_r, 0, nimg); cudaMemset(c->obs_ls, 0, nimg); cudaMemset(c->obs_rs, 0, nimg);
+  for (int cam = 0; cam < 2; ++cam) if (ts_alloc(c, cam)) return bail(ESVO_ERR_CUDA);
+  if (upload_tables(c)) return bail(ESVO_ERR_CUDA);
+  if (map_alloc_inputs(c, 16384, 512)) return bail(ESVO_ERR_CUDA);
+  if (fuse_alloc(c)) return bail(ESVO_ERR_CUDA);
+  if (track_alloc(c)) return bail(ESVO_ERR_CUDA);
+  if (status_out) *status_out = ESVO_OK;
+  return c;
+}
+
+ESVO_API void esvo_destroy(esvo_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int cam = 0; cam < 2; ++cam) ts_free(c, cam);
+  fuse_free(c);
+  track_free(c);
+  void* ps[] = {c->d_lut, c->d_mask, c->obs_l, c->obs_r, c->obs_ls, c->obs_rs, c->d_T_left_world, c->d_counters,
+                c->d_ex, c->d_ey, c->d_et, c->d_pose_t, c->d_poses, c->bm.flag, c->bm.disp, c->bm.pose_idx, c->bm.cost,
+                c->bm.xrect, c->d_seeds, c->lm_flag, c->lm_res, c->d_pts};
+  for (void* p : ps) if (p) cudaFree(p);
+  for (auto& f : c->win) { cudaFree(f.pts); cudaFree(f.cnt); }
+  for (auto& f : c->win_pool) { cudaFree(f.pts); cudaFree(f.cnt); }
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+ESVO_API int esvo_set_rectify_tables(esvo_ctx* c, int cam, const float* m1, const float* m2, const double* lut,
+                                     const uint8_t* mask) {
+  CHECK_CTX(c);
+  if (cam < 0 || cam > 1) return ESVO_ERR_INVALID_ARG;
+  const size_t n = (size_t)c->dc.W * c->dc.H;
+  if (m1) c->cam[cam].map1.assign(m1, m1 + n);
+  if (m2) c->cam[cam].map2.assign(m2, m2 + n);
+  if (lut) c->cam[cam].lut.assign(lut, lut + 2 * n);
+  if (mask) c->cam[cam].mask.assign(mask, mask + n);
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return upload_tables(c);
+}
+ESVO_API int esvo_get_rectify_tables(esvo_ctx* c, int cam, float* m1, float* m2, double* lut, uint8_t* mask) {
+  CHECK_CTX(c);
+  if (cam < 0 || cam > 1) return ESVO_ERR_INVALID_ARG;
+  const size_t n = (size_t)c->dc.W * c->dc.H;
+  if (m1) std::memcpy(m1, c->cam[cam].map1.data(), n * 4);
+  if (m2) std::memcpy(m2, c->cam[cam].map2.data(), n * 4);
+  if (lut) std::memcpy(lut, c->cam[cam].lut.data(), 2 * n * 8);
+  if (mask) std::memcpy(mask, c->cam[cam].mask.data(), n);
+  return ESVO_OK;
+}
+ESVO_API int esvo_get_derived(esvo_ctx* c, double out[4]) {
+  CHECK_CTX(c);
+  out[0] = c->dc.baseline; out[1] = c->dc.dmin; out[2] = c->dc.dmax; out[3] = c->dc.td_stdvar;
+  return ESVO_OK;
+}
+
+// ---------------- time surface ----------------
+ESVO_API int esvo_stage_ts_events(esvo_ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t,
+                                  const uint8_t* pol, size_t n) {
+  CHECK_CTX(c);
+  if (cam < 0 || cam > 1 || (n && (!x || !y || !t))) return ESVO_ERR_INVALID_ARG;
+  return ts_push(c, cam, x, y, t, pol, n);
+}
+ESVO_API int esvo_ts_push_events(esvo_ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t,
+                                 const uint8_t* pol, size_t n) {
+  int rc = esvo_stage_ts_events(c, cam, x, y, t, pol, n);
+  if (rc) return rc;
+  // the caller's buffers may be reused as soon as we return
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return ESVO_OK;
+}
+ESVO_API int esvo_run_ts_build(esvo_ctx* c, int cam, int64_t T) {
+  CHECK_CTX(c);
+  if (cam < 0 || cam > 1) return ESVO_ERR_INVALID_ARG;
+  return ts_run_build(c, cam, T);
+}
+ESVO_API int esvo_ts_build(esvo_ctx* c, int cam, int64_t T, int64_t* idx_out, uint8_t* ts_out) {
+  int rc = esvo_run_ts_build(c, cam, T);
+  if (rc) return rc;
+  TsState& s = c->ts[cam];
+  const DevConsts& d = c->dc;
+  if (idx_out) ESVO_CUDA_TRY(c, cudaMemcpyAsync(idx_out, s.out_idx, (size_t)d.W * d.H * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (ts_out) ESVO_CUDA_TRY(c, cudaMemcpy2DAsync(ts_out, d.W, s.img_out, d.pitch, d.W, d.H, cudaMemcpyDeviceToHost, c->stream));
+  int32_t sc[4] = {0, 0, 0, 0};
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(sc, s.scalars, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (sc[1]) { c->set_error("events were not pushed in time order (unsupported on the device path)"); return ESVO_ERR_UNSUPPORTED; }
+  return ESVO_OK;
+}
+ESVO_API int esvo_ts_reset(esvo_ctx* c, int cam) {
+  CHECK_CTX(c);
+  if (cam < 0 || cam > 1) return ESVO_ERR_INVALID_ARG;
+  return ts_reset_state(c, cam);
+}
+
+// ---------------- mapping ----------------
+ESVO_API int esvo_set_ts_pair(esvo_ctx* c, const uint8_t* l, const uint8_t* r, const double T[16]) {
+  CHECK_CTX(c);
+  if (!T) return ESVO_ERR_INVALID_ARG;
+  const DevConsts& d = c->dc;
+  const size_t nimg = (size_t)d.pitch * d.H;
+  if (l) ESVO_CUDA_TRY(c, cudaMemcpy2DAsync(c->obs_l, d.pitch, l, d.W, d.W, d.H, cudaMemcpyHostToDevice, c->stream));
+  else {
+    if (!c->ts[0].built) { c->set_error("ts_left == NULL but no time surface was built for camera 0"); return ESVO_ERR_STATE; }
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_l, c->ts[0].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (r) ESVO_CUDA_TRY(c, cudaMemcpy2DAsync(c->obs_r, d.pitch, r, d.W, d.W, d.H, cudaMemcpyHostToDevice, c->stream));
+  else {
+    if (!c->ts[1].built) { c->set_error("ts_right == NULL but no time surface was built for camera 1"); return ESVO_ERR_STATE; }
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_r, c->ts[1].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  std::memcpy(c->T_world_left, T, sizeof(c->T_world_left));
+  double Ti[16];
+  rigid_inverse(T, Ti);
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_T_left_world, Ti, sizeof(Ti), cudaMemcpyHostToDevice, c->stream));
+  // Until createMatchProblem smooths it, the observation the solver reads is the raw pair.
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_ls, c->obs_l, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_rs, c->obs_r, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // Ti and the caller's images are host stack/heap
+  c->obs_set = true;
+  return ESVO_OK;
+}
+
+static int run_bm_stage(esvo_ctx* c) {
+  if (c->prm.smooth_time_surface) { int rc = smooth_obs(c); if (rc) return rc; }  // EventBM.cpp:68-72
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(c->d_counters, 0, kCounters * 8, c->stream));
+  int rc = bm_run(c);
+  if (rc) return rc;
+  return seeds_order(c);
+}
+
+ESVO_API int esvo_bm_match(esvo_ctx* c, const uint16_t* ex, const uint16_t* ey, const int64_t* et, size_t n,
+                           const int64_t* pt, const double* poses, size_t np, esvo_seed* out, size_t* n_seeds,
+                           uint64_t* n_evals) {
+  CHECK_CTX(c);
+  if (!c->obs_set) return ESVO_ERR_STATE;
+  if (!n_seeds || (n && (!ex || !ey || !et))) return ESVO_ERR_INVALID_ARG;
+  int rc = stage_mapping(c, ex, ey, et, n, pt, poses, np);
+  if (rc) return rc;
+  if ((rc = run_bm_stage(c))) return rc;
+  if ((rc = fetch_counters(c))) return rc;
+  const size_t cnt = (size_t)c->h_counters[1];
+  if (n_evals) *n_evals = c->h_counters[5];
+  if (cnt > *n_seeds) { *n_seeds = cnt; return ESVO_ERR_CAPACITY; }
+  if (cnt) ESVO_CUDA_TRY(c, cudaMemcpy(out, c->d_seeds, cnt * sizeof(esvo_seed), cudaMemcpyDeviceToHost));
+  *n_seeds = cnt;
+  return ESVO_OK;
+}
+
+
+ESVO_API int esvo_depth_solve(esvo_ctx* c, const esvo_seed* seeds, size_t n, esvo_depth_point* out, size_t* n_out,
+                              uint64_t* n_evals) {
+  CHECK_CTX(c);
+  if (!c->obs_set) return ESVO_ERR_STATE;
+  if (!n_out || (n && !seeds)) return ESVO_ERR_INVALID_ARG;
+  if (n == 0) { *n_out = 0; if (n_evals) *n_evals = 0; return ESVO_OK; }
+  int rc = map_alloc_inputs(c, std::max(n, c->n_ev), c->n_poses);
+  if (rc) return rc;
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_seeds, seeds, n * sizeof(esvo_seed), cudaMemcpyHostToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(c->d_counters, 0, kCounters * 8, c->stream));
+  if ((rc = lm_run(c, c->d_seeds, n))) return rc;
+  if ((rc = points_order_impl(c, c->d_seeds, n, 0, 0, 0, 0, 0, nullptr, nullptr))) return rc;
+  if ((rc = fetch_counters(c))) return rc;
+  const size_t cnt = (size_t)c->h_counters[3];
+  if (n_evals) *n_evals = c->h_counters[6];
+  if (cnt > *n_out) { *n_out = cnt; return ESVO_ERR_CAPACITY; }
+  if (cnt) ESVO_CUDA_TRY(c, cudaMemcpy(out, c->d_pts, cnt * sizeof(esvo_depth_point), cudaMemcpyDeviceToHost));
+  *n_out = cnt;
+  return ESVO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+// esvo_b200 product code -- C ABI, part 2: culling, fusion, map and whole-frame mapping entry points.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace esvo {
+int fuse_zero_fusion_counter(Ctx* c);
+int fuse_fetch_scalars(Ctx* c, unsigned long long out[4]);
+
+template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+static int win_acquire(Ctx* c, size_t cap, Ctx::WinFrame& f) {
+  for (size_t i = 0; i < c->win_pool.size(); ++i)
+    if (c->win_pool[i].cap >= cap) { f = c->win_pool[i]; c->win_pool.erase(c->win_pool.begin() + i); return ESVO_OK; }
+  f = Ctx::WinFrame();
+  f.cap = std::max<size_t>(cap, 1024);
+  ESVO_CUDA_TRY(c, dmalloc(&f.pts, f.cap));
+  ESVO_CUDA_TRY(c, dmalloc(&f.cnt, 1));
+  return ESVO_OK;
+}
+
+static int fetch_counters2(Ctx* c) {
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->d_counters, kCounters * 8, cudaMemcpyDeviceToHost, c->stream));
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return ESVO_OK;
+}
+
+// esvo_Mapping::MappingAtTime (esvo_Mapping.cpp:261-399), kernels only, everything stays on the device.
+static int run_mapping_frame(Ctx* c) {
+  const esvo_params& p = c->prm;
+  int rc;
+  if (p.smooth_time_surface && (rc = smooth_obs(c))) return rc;           // createMatchProblem (EventBM.cpp:68-72)
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(c->d_counters, 0, kCounters * 8, c->stream));
+  if ((rc = bm_run(c))) return rc;                                        // :308-309
+  if ((rc = seeds_order(c))) return rc;
+  if ((rc = lm_run(c, c->d_seeds, 0))) return rc;                         // :330
+  Ctx::WinFrame f;
+  if ((rc = win_acquire(c, std::max<size_t>(c->n_ev, 1), f))) return rc;
+  const double cost_thr = p.residual_vis_threshold * p.residual_vis_threshold * (double)(p.patch_size_x * p.patch_size_y);
+  if ((rc = points_order_impl(c, c->d_seeds, 0, 1, p.stdvar_vis_threshold, cost_thr, p.invdepth_min_range,
+                              p.invdepth_max_range, f.pts, f.cnt)))       // :334 pointCulling
+    return rc;
+  c->win.push_back(f);                                                    // :342-368
+  if (p.fusion_strategy == ESVO_FUSION_CONST_POINTS) {
+    // needs the per-frame counts on the host: one small D2H per frame (the reference's CONST_FRAMES cfgs avoid it)
+    auto total = [&](size_t& tot) -> int {
+      tot = 0;
+      for (auto& w : c->win) {
+        unsigned long long n = 0;
+        ESVO_CUDA_TRY(c, cudaMemcpyAsync(&n, w.cnt, 8, cudaMemcpyDeviceToHost, c->stream));
+        ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        tot += (size_t)n;
+      }
+      return ESVO_OK;
+    };
+    size_t tot;
+    if ((rc = total(tot))) return rc;
+    while ((double)tot > 1.5 * p.max_num_fusion_points && !c->win.empty()) {
+      c->win_pool.push_back(c->win.front()); c->win.erase(c->win.begin());
+      if ((rc = total(tot))) return rc;
+    }
+  } else {
+    while (c->win.size() > (size_t)p.max_num_fusion_frames) { c->win_pool.push_back(c->win.front()); c->win.erase(c->win.begin()); }
+  }
+  if ((rc = fuse_reset_map(c, c->T_world_left))) return rc;               // :268-272 fresh DepthFrame at the obs pose
+  if ((rc = fuse_zero_fusion_counter(c))) return rc;
+  for (auto it = c->win.rbegin(); it != c->win.rend(); ++it)              // :372-377 newest first
+    if ((rc = fuse_points(c, it->pts, it->cap, (const uint64_t*)it->cnt, p.fusion_radius, 0))) return rc;
+  if ((rc = fuse_finish(c))) return rc;
+  if (c->win.size() >= (size_t)p.max_num_fusion_frames)                   // :385-386
+    if ((rc = map_clean(c, p.stdvar_vis_threshold * p.stdvar_vis_threshold, p.age_vis_threshold, p.invdepth_max_range,
+                        p.invdepth_min_range)))
+      return rc;
+  if (p.regularization && (rc = map_regularize(c))) return rc;            // :390-395
+  return map_count(c);
+}
+
+static int fetch_mapping_counters(Ctx* c, uint64_t out[8]) {
+  int rc = fetch_counters2(c);
+  if (rc) return rc;
+  unsigned long long sc[4];
+  if ((rc = fuse_fetch_scalars(c, sc))) return rc;
+  out[0] = c->n_ev; out[1] = c->h_counters[1]; out[2] = c->h_counters[2]; out[3] = c->h_counters[3];
+  out[4] = sc[0]; out[5] = c->h_counters[5]; out[6] = c->h_counters[6]; out[7] = sc[2];
+  return ESVO_OK;
+}
+}  // namespace esvo
+
+using namespace esvo;
+#define CHECK_CTX(c) do { if (!(c)) return ESVO_ERR_INVALID_ARG; cudaSetDevice((c)->device); } while (0)
+
+extern "C" {
+
+ESVO_API int esvo_depth_cull(esvo_ctx* c, esvo_depth_point* pts, size_t* n, double std_thr, double cost_thr,
+                             double rmin, double rmax) {
+  CHECK_CTX(c);
+  if (!n || (*n && !pts)) return ESVO_ERR_INVALID_ARG;
+  if (*n == 0) return ESVO_OK;
+  int rc = map_alloc_inputs(c, std::max(*n, c->n_ev), c->n_poses);
+  if (rc) return rc;
+  esvo_depth_point* tmp = nullptr;
+  ESVO_CUDA_TRY(c, dmalloc(&tmp, *n));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(tmp, pts, *n * sizeof(esvo_depth_point), cudaMemcpyHostToDevice, c->stream));
+  rc = cull_points(c, tmp, *n, std_thr, cost_thr, rmin, rmax);
+  if (!rc) rc = fetch_counters2(c);
+  if (!rc) {
+    const size_t cnt = (size_t)c->h_counters[3];
+    if (cnt) cudaMemcpy(pts, c->d_pts, cnt * sizeof(esvo_depth_point), cudaMemcpyDeviceToHost);
+    *n = cnt;
+  }
+  cudaFree(tmp);
+  return rc;
+}
+
+ESVO_API int esvo_fuse(esvo_ctx* c, const esvo_depth_point* pts, size_t n, const double T[16], int radius, int reset_map,
+                       int* n_fusions) {
+  CHECK_CTX(c);
+  if (n && !pts) return ESVO_ERR_INVALID_ARG;
+  int rc;
+  if (reset_map) { if (!T) return ESVO_ERR_INVALID_ARG; if ((rc = fuse_reset_map(c, T))) return rc; }
+  if ((rc = fuse_zero_fusion_counter(c))) return rc;
+  esvo_depth_point* tmp = nullptr;
+  if (n) {
+    ESVO_CUDA_TRY(c, dmalloc(&tmp, n));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(tmp, pts, n * sizeof(esvo_depth_point), cudaMemcpyHostToDevice, c->stream));
+    rc = fuse_points(c, tmp, n, nullptr, radius, 0);
+    if (!rc) rc = fuse_finish(c);
+  }
+  unsigned long long sc[4] = {0, 0, 0, 0};
+  if (!rc) rc = fuse_fetch_scalars(c, sc);
+  if (tmp) cudaFree(tmp);
+  if (n_fusions) *n_fusions = (int)sc[0];
+  return rc;
+}
+
+ESVO_API int esvo_map_clean(esvo_ctx* c, double var_thr, double age_thr, double rmax, double rmin) {
+  CHECK_CTX(c);
+  return map_clean(c, var_thr, age_thr, rmax, rmin);
+}
+ESVO_API int esvo_map_regularize(esvo_ctx* c) { CHECK_CTX(c); return map_regularize(c); }
+ESVO_API int esvo_map_download(esvo_ctx* c, esvo_depth_point* out, size_t* n) {
+  CHECK_CTX(c);
+  if (!n) return ESVO_ERR_INVALID_ARG;
+  return map_download(c, out, n);
+}
+ESVO_API int esvo_mapping_reset(esvo_ctx* c) {
+  CHECK_CTX(c);
+  for (auto& f : c->win) c->win_pool.push_back(f);
+  c->win.clear();
+  return ESVO_OK;
+}
+
+ESVO_API int esvo_stage_mapping_inputs(esvo_ctx* c, const uint16_t* ex, const uint16_t* ey, const int64_t* et, size_t n,
+                                       const int64_t* pt, const double* poses, size_t np) {
+  CHECK_CTX(c);
+  if (n && (!ex || !ey || !et)) return ESVO_ERR_INVALID_ARG;
+  if (np && (!pt || !poses)) return ESVO_ERR_INVALID_ARG;
+  int rc = map_alloc_inputs(c, n, np);
+  if (rc) return rc;
+  c->n_ev = n; c->n_poses = np;
+  if (n) {
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ex, ex, n * 2, cudaMemcpyHostToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ey, ey, n * 2, cudaMemcpyHostToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_et, et, n * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (np) {
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_pose_t, pt, np * 8, cudaMemcpyHostToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_poses, poses, np * 16 * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  return ESVO_OK;
+}
+ESVO_API int esvo_run_mapping(esvo_ctx* c) {
+  CHECK_CTX(c);
+  if (!c->obs_set) return ESVO_ERR_STATE;
+  return run_mapping_frame(c);
+}
+ESVO_API int esvo_fetch_mapping_counters(esvo_ctx* c, uint64_t out[8]) {
+  CHECK_CTX(c);
+  return fetch_mapping_counters(c, out);
+}
+ESVO_API int esvo_mapping_at_time(esvo_ctx* c, const uint16_t* ex, const uint16_t* ey, const int64_t* et, size_t n,
+                                  const int64_t* pt, const double* poses, size_t np, uint64_t* counters) {
+  int rc = esvo_stage_mapping_inputs(c, ex, ey, et, n, pt, poses, np);
+  if (rc) return rc;
+  if ((rc = esvo_run_mapping(c))) return rc;
+  uint64_t ctr[8];
+  if ((rc = fetch_mapping_counters(c, ctr))) return rc;   // also the sync that makes the caller's buffers reusable
+  if (counters) std::memcpy(counters, ctr, sizeof(ctr));
+  return ESVO_OK;
+}
+
+}  // extern "C"

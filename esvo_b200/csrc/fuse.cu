@@ -1,0 +1,480 @@
+// esvo_b200 product code -- depth propagation, Student-t fusion, map clean-up and regularisation
+// (sm_100a).
+//
+// Replaces esvo_core::core::DepthFusion::{propagate_one_point, fusion, update, boundaryCheck,
+// chiSquareTest, studentTCompatibleTest} (esvo_core/src/core/DepthFusion.cpp:18-231),
+// DepthPoint::{update, update_studentT} (esvo_core/src/container/DepthPoint.cpp:145-188),
+// SmartGrid::{set, clean, getNeighbourhood} (esvo_core/include/esvo_core/container/SmartGrid.h)
+// and DepthRegularization::apply (esvo_core/src/core/DepthRegularization.cpp:19-110).
+//
+// The reference folds the propagated points into the map strictly one after another; the result
+// at a pixel depends on the ORDER of the points that touch it, not on points touching other
+// pixels.  So: (1) every point is propagated independently (one thread per point) and appends
+// its 2x2 / 3x3 splat to a per-pixel linked list (one atomicExch per touched pixel);
+// (2) one thread per pixel replays its own list in the global sequence order (list ids are the
+// sequence numbers).  The map is a dense SoA over the image (the SmartGrid's element list order
+// is kept as a "first touched" sequence number per pixel).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace esvo {
+
+struct MapSoA {
+  uint8_t* exists;
+  double *rho, *s2, *nu, *var, *res, *x0, *x1, *pc0, *pc1, *pc2, *rho_tmp;
+  long long* age;
+  int32_t *row, *col;
+  unsigned long long* first_key;
+};
+struct PropSoA {  // propagated points staged for the current fold
+  uint8_t* ok;
+  double *rho, *s2, *nu, *var, *res, *x0, *x1, *pc0, *pc1, *pc2;
+  long long* age;
+  int32_t *row, *col;
+};
+struct MapState {
+  MapSoA m;
+  PropSoA p;
+  size_t prop_cap = 0, staged = 0;
+  int32_t* head = nullptr;       // per pixel, -1 = empty
+  int32_t* next = nullptr;       // per contribution (9 per staged point)
+  unsigned long long seq_base = 0;
+  double T_world_frame[16];
+  double T_frame_world[16];
+  double* d_T_frame_world = nullptr;
+  esvo_depth_point* d_dl = nullptr;      // download staging
+  unsigned long long* d_dl_keys = nullptr;
+  unsigned long long* d_scal = nullptr;  // [0] n_fusions, [1] download count
+  unsigned long long* h_scal = nullptr;
+};
+
+template <class T> static cudaError_t dm(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+__device__ __forceinline__ void cam2world_f(const DevConsts& dc, double x, double y, double rho, double& p0, double& p1, double& p2) {
+  const double z = 1.0 / rho;
+  p0 = (x - dc.cx - dc.Pl[3] / z) * z / dc.fx;
+  p1 = (y - dc.cy - dc.Pl[7] / z) * z / dc.fy;
+  p2 = z * (1.0 - dc.Pl[11] / z);
+}
+
+// ---- stage: propagate_one_point (:18-68) + splat list insertion (:97-121) ----
+__global__ void fuse_stage_kernel(DevConsts dc, const esvo_depth_point* __restrict__ pts, int n_fixed,
+                                  const unsigned long long* __restrict__ n_ptr, const double* __restrict__ T_frame_world,
+                                  int radius, int stage_off, PropSoA P, int32_t* head, int32_t* next) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = n_ptr ? (int)*n_ptr : n_fixed;
+  if (j >= n) return;
+  const esvo_depth_point& d = pts[j];
+  const int sid = stage_off + j;
+  // T_frame_obs = T_frame_world * T_world_cam
+  double T[12];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += T_frame_world[r * 4 + k] * d.T_world_cam[k * 4 + c];
+      T[r * 4 + c] = s;
+    }
+  double pp[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) pp[r] = T[r * 4] * d.p_cam[0] + T[r * 4 + 1] * d.p_cam[1] + T[r * 4 + 2] * d.p_cam[2] + T[r * 4 + 3];
+  double h[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) h[r] = dc.Pl[r * 4] * pp[0] + dc.Pl[r * 4 + 1] * pp[1] + dc.Pl[r * 4 + 2] * pp[2] + dc.Pl[r * 4 + 3];
+  const double xp = h[0] / h[2], yp = h[1] / h[2];
+  const bool inb = !(xp < 0 || xp >= dc.W || yp < 0 || yp >= dc.H);  // boundaryCheck; NaN -> "inside" like the reference...
+  if (!inb || !(xp == xp) || !(yp == yp)) { P.ok[sid] = 0; return; }  // ...but a NaN pixel index is UB there; drop it
+  const int row = (int)floor(yp), col = (int)floor(xp);
+  const double invDepth = 1.0 / pp[2];
+  double den = T[8] * d.p_cam[0] + T[9] * d.p_cam[1] + T[11];
+  den /= d.p_cam[2];
+  den += T[10];
+  const double J = T[10] / (den * den);
+  P.ok[sid] = 1; P.row[sid] = row; P.col[sid] = col; P.x0[sid] = xp; P.x1[sid] = yp; P.rho[sid] = invDepth;
+  if (dc.lsnorm == ESVO_LSNORM_L2) {
+    double var = J * J * d.variance;
+    if (var < 1e-6) var = 1e-6;  // DepthPoint::update -> boundVariance
+    P.var[sid] = var; P.s2[sid] = 0; P.nu[sid] = 0;
+  } else {
+    const double s2 = J * J * d.scale2, nu = d.nu;
+    P.s2[sid] = s2; P.nu[sid] = nu; P.var[sid] = nu / (nu - 2) * s2;
+  }
+  P.pc0[sid] = pp[0]; P.pc1[sid] = pp[1]; P.pc2[sid] = pp[2];
+  P.res[sid] = d.residual; P.age[sid] = d.age;
+  const int lo = radius == 0 ? 0 : -1;
+  int i = 0;
+  for (int dy = lo; dy <= 1; ++dy)
+    for (int dx = lo; dx <= 1; ++dx, ++i) {
+      const int r = row + dy, c = col + dx;
+      if (r < 0 || c < 0 || r >= dc.H || c >= dc.W) continue;
+      const int cid = sid * 9 + i;
+      next[cid] = atomicExch(&head[(size_t)r * dc.W + c], cid);
+    }
+}
+
+// ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
+__global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* head, const int32_t* __restrict__ next,
+                                 unsigned long long seq_base, unsigned long long* scal) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= dc.W * dc.H) return;
+  int h = head[pix];
+  if (h < 0) return;
+  head[pix] = -1;
+  // The list is in reverse insertion order of the atomics, not in sequence order: collect and sort.
+  constexpr int CAP = 48;
+  int ids[CAP];
+  int cnt = 0, total = 0;
+  for (int q = h; q >= 0; q = next[q]) { if (cnt < CAP) ids[cnt++] = q; ++total; }
+  const int row = pix / dc.W, col = pix - row * dc.W;
+  bool ex = M.exists[pix] != 0;
+  double rho = 0, s2 = 0, nu = 0, var = 0, res = 0, x0 = 0, x1 = 0, pc0 = 0, pc1 = 0, pc2 = 0;
+  long long age = 0; int erow = row, ecol = col;
+  unsigned long long fkey = 0;
+  if (ex) {
+    rho = M.rho[pix]; s2 = M.s2[pix]; nu = M.nu[pix]; var = M.var[pix]; res = M.res[pix]; x0 = M.x0[pix]; x1 = M.x1[pix];
+    pc0 = M.pc0[pix]; pc1 = M.pc1[pix]; pc2 = M.pc2[pix]; age = M.age[pix]; erow = M.row[pix]; ecol = M.col[pix];
+    fkey = M.first_key[pix];
+  }
+  int nfus = 0;
+  auto apply = [&](int cid) {
+    const int sid = cid / 9;
+    const double prho = P.rho[sid], ps2 = P.s2[sid], pnu = P.nu[sid], pvar = P.var[sid], pres = P.res[sid];
+    if (!ex) {  // case 1 (:126-145)
+      ex = true; erow = row; ecol = col; x0 = col + 0.5; x1 = row + 0.5;
+      rho = prho; var = pvar; s2 = ps2; nu = pnu;
+      if (dc.lsnorm == ESVO_LSNORM_L2 && var < 1e-6) var = 1e-6;
+      res = pres; age = P.age[sid];
+      cam2world_f(dc, x0, x1, prho, pc0, pc1, pc2);
+      fkey = seq_base + (unsigned long long)cid;
+      return;
+    }
+    bool compat;
+    if (dc.lsnorm == ESVO_LSNORM_L2) {
+      const double d2 = (prho - rho) * (prho - rho);
+      compat = (d2 / pvar + d2 / var) < 5.99;
+    } else {
+      const double diff = fabs(prho - rho);
+      compat = diff < 2 * sqrt(pvar) || diff < 2 * sqrt(var);
+    }
+    if (compat) {  // case 2.1 (:162-177)
+      if (dc.lsnorm == ESVO_LSNORM_L2) {
+        const double t = rho;
+        rho = (var * prho + pvar * t) / (var + pvar);
+        const double tv = var;
+        var = (tv * pvar) / (tv + pvar);
+        if (var < 1e-6) var = 1e-6;
+      } else {
+        const double nu_u = fmin(pnu, nu);
+        const double rho_u = (ps2 * rho + s2 * prho) / (s2 + ps2);
+        const double dd = rho - prho;
+        const double s2_u = (nu_u + (dd * dd) / (s2 + ps2)) / (nu_u + 1) * (s2 * ps2) / (s2 + ps2);
+        rho = rho_u; s2 = s2_u; nu = nu_u + 1;
+        var = nu / (nu - 2) * s2;
+        age++;                                   // DepthPoint.cpp:179
+      }
+      age++;                                     // DepthFusion.cpp:171
+      res = fmin(res, pres);
+      cam2world_f(dc, x0, x1, prho, pc0, pc1, pc2);   // p_cam from the PROPAGATED rho (:174)
+      nfus++;
+    } else {       // case 2.2 (:178-188)
+      if (rho - 2 * sqrt(var) > prho) return;
+      if (pvar < var && pres < res) {              // dm->get(row,col) = dp_prop
+        rho = prho; s2 = ps2; nu = pnu; var = pvar; res = pres; age = P.age[sid];
+        x0 = P.x0[sid]; x1 = P.x1[sid]; pc0 = P.pc0[sid]; pc1 = P.pc1[sid]; pc2 = P.pc2[sid];
+        erow = P.row[sid]; ecol = P.col[sid];
+      }
+    }
+  };
+  if (total <= CAP) {
+    for (int a = 1; a < cnt; ++a) { int v = ids[a], b = a - 1; while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; } ids[b + 1] = v; }
+    for (int a = 0; a < cnt; ++a) apply(ids[a]);
+  } else {  // long list: repeated minimum selection, O(L^2) walks, no storage
+    int last = -1;
+    for (int a = 0; a < total; ++a) {
+      int best = 0x7fffffff;
+      for (int q = h; q >= 0; q = next[q]) if (q > last && q < best) best = q;
+      apply(best);
+      last = best;
+    }
+  }
+  M.exists[pix] = ex ? 1 : 0;
+  M.rho[pix] = rho; M.s2[pix] = s2; M.nu[pix] = nu; M.var[pix] = var; M.res[pix] = res; M.x0[pix] = x0; M.x1[pix] = x1;
+  M.pc0[pix] = pc0; M.pc1[pix] = pc1; M.pc2[pix] = pc2; M.age[pix] = age; M.row[pix] = erow; M.col[pix] = ecol;
+  M.first_key[pix] = fkey;
+  if (nfus) atomicAdd(&scal[0], (unsigned long long)nfus);
+}
+
+// ---- SmartGrid::clean (:222-243) ----
+__global__ void map_clean_kernel(int npix, MapSoA M, double var_thr, double age_thr, double rmax, double rmin) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix || !M.exists[pix]) return;
+  const double rho = M.rho[pix];
+  const bool valid = rho > -1e-6 && (double)M.age[pix] >= age_thr && M.var[pix] <= var_thr && rho <= rmax && rho >= rmin;
+  if (!valid) M.exists[pix] = 0;
+}
+
+// ---- DepthRegularization::apply ----
+__global__ void map_regularize_kernel(DevConsts dc, MapSoA M, int radius, int min_nb, int min_close) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= dc.W * dc.H) return;
+  if (!M.exists[pix]) return;
+  const double rho = M.rho[pix];
+  M.rho_tmp[pix] = rho;
+  if (!(rho > -1e-6)) return;
+  const int row = pix / dc.W, col = pix - row * dc.W;
+  const double sig = 2.0 * sqrt(M.var[pix]);
+  bool isSet = false;
+  double mean = 0;
+  // SmartGrid::getNeighbourhood's int/size_t loop never runs when row<radius or col<radius (SmartGrid.h:373-375)
+  if (row >= radius && col >= radius) {
+    int nb = 0, nclose = 0;
+    double nu_post = 0, rho_post = 0, s2_post = 0, tot = 0;
+    // pass 1: counts (+ l2 total inverse variance)
+    for (int r = row - radius; r <= row + radius; ++r) {
+      if (r >= dc.H) break;
+      for (int c = col - radius; c <= col + radius; ++c) {
+        if (c >= dc.W) break;
+        const int q = r * dc.W + c;
+        if (!M.exists[q]) continue;
+        const double qr = M.rho[q];
+        if (!(qr > -1e-6)) continue;
+        nb++;
+        const double diff = fabs(rho - qr);
+        if (diff < sig || diff < 2.0 * sqrt(M.var[q])) {
+          if (dc.lsnorm == ESVO_LSNORM_L2) tot += 1.0 / M.var[q];
+          else if (nclose == 0) { nu_post = M.nu[q]; rho_post = qr; s2_post = M.s2[q]; }
+          else {
+            const double nu_prior = nu_post, rho_prior = rho_post, s2_prior = s2_post;
+            const double nu_obs = M.nu[q], rho_obs = qr, s2_obs = M.s2[q];
+            nu_post = fmin(nu_prior, nu_obs);
+            rho_post = (s2_obs * rho_prior + s2_prior * rho_obs) / (s2_obs + s2_prior);
+            const double d = rho_prior - rho_obs;
+            s2_post = (nu_post + (d * d) / (s2_prior + s2_obs)) / (nu_post + 1) * (s2_prior * s2_obs) / (s2_prior + s2_obs);
+          }
+          nclose++;
+        }
+      }
+    }
+    if (nb > min_nb && nclose > min_close) {
+      if (dc.lsnorm == ESVO_LSNORM_L2) {
+        for (int r = row - radius; r <= row + radius && r < dc.H; ++r)
+          for (int c = col - radius; c <= col + radius && c < dc.W; ++c) {
+            const int q = r * dc.W + c;
+            if (!M.exists[q]) continue;
+            const double qr = M.rho[q];
+            if (!(qr > -1e-6)) continue;
+            const double diff = fabs(rho - qr);
+            if (diff < sig || diff < 2.0 * sqrt(M.var[q])) mean += qr * (1.0 / M.var[q]) / tot;
+          }
+      } else mean = rho_post;
+      isSet = true;
+    }
+  }
+  M.rho_tmp[pix] = isSet ? mean : -1.0;
+}
+__global__ void map_regularize_commit_kernel(int npix, MapSoA M) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < npix && M.exists[pix]) M.rho[pix] = M.rho_tmp[pix];
+}
+
+// ---- download: compact existing pixels (unordered) with their creation keys ----
+__global__ void map_gather_kernel(DevConsts dc, MapSoA M, const double* __restrict__ Twf, esvo_depth_point* out,
+                                  unsigned long long* keys, unsigned long long* scal) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= dc.W * dc.H || !M.exists[pix]) return;
+  const unsigned long long pos = atomicAdd(&scal[1], 1ULL);
+  esvo_depth_point d;
+  d.row = M.row[pix]; d.col = M.col[pix]; d.x[0] = M.x0[pix]; d.x[1] = M.x1[pix]; d.inv_depth = M.rho[pix];
+  d.scale2 = M.s2[pix]; d.nu = M.nu[pix]; d.variance = M.var[pix]; d.residual = M.res[pix]; d.age = M.age[pix];
+  d.p_cam[0] = M.pc0[pix]; d.p_cam[1] = M.pc1[pix]; d.p_cam[2] = M.pc2[pix];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) d.T_world_cam[q] = Twf[q];
+  out[pos] = d;
+  keys[pos] = M.first_key[pix];
+}
+__global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// --------------------------------------------------------------------------------------------
+static int prop_reserve(Ctx* c, size_t need) {
+  MapState* ms = c->map;
+  if (need <= ms->prop_cap) return ESVO_OK;
+  if (ms->staged) { c->set_error("internal: staging buffer grown while points are staged"); return ESVO_ERR_STATE; }
+  size_t cap = std::max<size_t>(need, 65536);
+  PropSoA& P = ms->p;
+  void* olds[] = {P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col, ms->next};
+  for (void* p : olds) if (p) cudaFree(p);
+  ESVO_CUDA_TRY(c, dm(&P.ok, cap));
+  double** ds[] = {&P.rho, &P.s2, &P.nu, &P.var, &P.res, &P.x0, &P.x1, &P.pc0, &P.pc1, &P.pc2};
+  for (double** d : ds) ESVO_CUDA_TRY(c, dm(d, cap));
+  ESVO_CUDA_TRY(c, dm(&P.age, cap)); ESVO_CUDA_TRY(c, dm(&P.row, cap)); ESVO_CUDA_TRY(c, dm(&P.col, cap));
+  ESVO_CUDA_TRY(c, dm(&ms->next, cap * 9));
+  ms->prop_cap = cap;
+  return ESVO_OK;
+}
+
+int fuse_alloc(Ctx* c) {
+  MapState* ms = new MapState();
+  c->map = ms;
+  const size_t npix = (size_t)c->dc.W * c->dc.H;
+  MapSoA& M = ms->m;
+  std::memset(&M, 0, sizeof(M)); std::memset(&ms->p, 0, sizeof(ms->p));
+  ESVO_CUDA_TRY(c, dm(&M.exists, npix));
+  double** ds[] = {&M.rho, &M.s2, &M.nu, &M.var, &M.res, &M.x0, &M.x1, &M.pc0, &M.pc1, &M.pc2, &M.rho_tmp};
+  for (double** d : ds) ESVO_CUDA_TRY(c, dm(d, npix));
+  ESVO_CUDA_TRY(c, dm(&M.age, npix)); ESVO_CUDA_TRY(c, dm(&M.row, npix)); ESVO_CUDA_TRY(c, dm(&M.col, npix));
+  ESVO_CUDA_TRY(c, dm(&M.first_key, npix));
+  ESVO_CUDA_TRY(c, dm(&ms->head, npix));
+  ESVO_CUDA_TRY(c, dm(&ms->d_T_frame_world, 32));
+  ESVO_CUDA_TRY(c, dm(&ms->d_dl, npix)); ESVO_CUDA_TRY(c, dm(&ms->d_dl_keys, npix));
+  ESVO_CUDA_TRY(c, dm(&ms->d_scal, 4));
+  ESVO_CUDA_TRY(c, cudaMallocHost((void**)&ms->h_scal, 4 * 8));
+  ESVO_CUDA_TRY(c, cudaMemset(M.exists, 0, npix));
+  ESVO_CUDA_TRY(c, cudaMemset(ms->head, 0xff, npix * 4));
+  ESVO_CUDA_TRY(c, cudaMemset(ms->d_scal, 0, 4 * 8));
+  for (int i = 0; i < 16; ++i) ms->T_world_frame[i] = ms->T_frame_world[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  ESVO_CUDA_TRY(c, cudaMemcpy(ms->d_T_frame_world, ms->T_frame_world, 128, cudaMemcpyHostToDevice));
+  ESVO_CUDA_TRY(c, cudaMemcpy(ms->d_T_frame_world + 16, ms->T_world_frame, 128, cudaMemcpyHostToDevice));
+  return prop_reserve(c, 65536);
+}
+void fuse_free(Ctx* c) {
+  MapState* ms = c->map;
+  if (!ms) return;
+  MapSoA& M = ms->m; PropSoA& P = ms->p;
+  void* ps[] = {M.exists, M.rho, M.s2, M.nu, M.var, M.res, M.x0, M.x1, M.pc0, M.pc1, M.pc2, M.rho_tmp, M.age, M.row, M.col,
+                M.first_key, P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col,
+                ms->head, ms->next, ms->d_T_frame_world, ms->d_dl, ms->d_dl_keys, ms->d_scal};
+  for (void* p : ps) if (p) cudaFree(p);
+  if (ms->h_scal) cudaFreeHost(ms->h_scal);
+  delete ms;
+  c->map = nullptr;
+}
+
+int fuse_reset_map(Ctx* c, const double T[16]) {
+  MapState* ms = c->map;
+  const size_t npix = (size_t)c->dc.W * c->dc.H;
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->m.exists, 0, npix, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->head, 0xff, npix * 4, c->stream));
+  std::memcpy(ms->T_world_frame, T, 128);
+  // rigid inverse (kindr Transformation::inverse)
+  double* I = ms->T_frame_world;
+  for (int i = 0; i < 16; ++i) I[i] = 0;
+  I[15] = 1;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) I[i * 4 + j] = T[j * 4 + i];
+  for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += I[i * 4 + k] * T[k * 4 + 3]; I[i * 4 + 3] = -s; }
+  // pageable host source: cudaMemcpyAsync returns after staging, safe to reuse the members
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(ms->d_T_frame_world, ms->T_frame_world, 128, cudaMemcpyHostToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(ms->d_T_frame_world + 16, ms->T_world_frame, 128, cudaMemcpyHostToDevice, c->stream));
+  ms->seq_base = 0; ms->staged = 0;
+  return ESVO_OK;
+}
+
+// Stage one vector of DepthPoints (device array).  n_cap bounds the count when it lives on the device.
+int fuse_points(Ctx* c, const esvo_depth_point* d_pts, size_t n_cap, const uint64_t* d_n, int radius, int) {
+  MapState* ms = c->map;
+  if (n_cap == 0) return ESVO_OK;
+  if (ms->staged + n_cap > ms->prop_cap) {
+    if (ms->staged) { c->set_error("fusion staging capacity exceeded"); return ESVO_ERR_CAPACITY; }
+    int rc = prop_reserve(c, n_cap);
+    if (rc) return rc;
+  }
+  const int B = 128;
+  fuse_stage_kernel<<<div_up((int)n_cap, B), B, 0, c->stream>>>(c->dc, d_pts, (int)n_cap, (const unsigned long long*)d_n,
+                                                                ms->d_T_frame_world, radius, (int)ms->staged, ms->p,
+                                                                ms->head, ms->next);
+  c->launches += 1;
+  ms->staged += n_cap;
+  ESVO_CUDA_TRY(c, cudaGetLastError());
+  return ESVO_OK;
+}
+
+int fuse_finish(Ctx* c) {
+  MapState* ms = c->map;
+  if (ms->staged == 0) return ESVO_OK;
+  const int npix = c->dc.W * c->dc.H, B = 128;
+  fuse_fold_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->seq_base, ms->d_scal);
+  c->launches += 1;
+  ms->seq_base += (unsigned long long)ms->staged * 9ULL;
+  ms->staged = 0;
+  ESVO_CUDA_TRY(c, cudaGetLastError());
+  return ESVO_OK;
+}
+
+int map_clean(Ctx* c, double var_thr, double age_thr, double rmax, double rmin) {
+  const int npix = c->dc.W * c->dc.H, B = 256;
+  map_clean_kernel<<<div_up(npix, B), B, 0, c->stream>>>(npix, c->map->m, var_thr, age_thr, rmax, rmin);
+  c->launches += 1;
+  return ESVO_OK;
+}
+
+int map_regularize(Ctx* c) {
+  const int npix = c->dc.W * c->dc.H, B = 128;
+  map_regularize_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, c->map->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
+                                                              c->prm.reg_min_close_neighbours);
+  map_regularize_commit_kernel<<<div_up(npix, 256), 256, 0, c->stream>>>(npix, c->map->m);
+  c->launches += 2;
+  return ESVO_OK;
+}
+
+int map_download(Ctx* c, esvo_depth_point* out, size_t* n) {
+  MapState* ms = c->map;
+  const int npix = c->dc.W * c->dc.H, B = 128;
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->d_scal + 1, 0, 8, c->stream));
+  map_gather_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->d_T_frame_world + 16, ms->d_dl, ms->d_dl_keys, ms->d_scal);
+  c->launches += 1;
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(ms->h_scal, ms->d_scal, 32, cudaMemcpyDeviceToHost, c->stream));
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const size_t cnt = (size_t)ms->h_scal[1];
+  if (cnt > *n) { *n = cnt; return ESVO_ERR_CAPACITY; }
+  // Host marshalling: restore SmartGrid's list order (creation sequence) while copying out.
+  std::vector<esvo_depth_point> tmp(cnt);
+  std::vector<unsigned long long> keys(cnt);
+  if (cnt) {
+    ESVO_CUDA_TRY(c, cudaMemcpy(tmp.data(), ms->d_dl, cnt * sizeof(esvo_depth_point), cudaMemcpyDeviceToHost));
+    ESVO_CUDA_TRY(c, cudaMemcpy(keys.data(), ms->d_dl_keys, cnt * 8, cudaMemcpyDeviceToHost));
+  }
+  std::vector<uint32_t> ord(cnt);
+  for (size_t i = 0; i < cnt; ++i) ord[i] = (uint32_t)i;
+  std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+  for (size_t i = 0; i < cnt; ++i) out[i] = tmp[ord[i]];
+  *n = cnt;
+  return ESVO_OK;
+}
+
+}  // namespace esvo
+
+namespace esvo {
+__global__ void map_count_kernel(int npix, MapSoA M, unsigned long long* scal) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = (pix < npix && M.exists[pix]) ? 1 : 0;
+  const int s = warp_sum_i(e);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(&scal[2], (unsigned long long)s);
+}
+// counts existing map pixels into scal[2]
+int map_count(Ctx* c) {
+  MapState* ms = c->map;
+  const int npix = c->dc.W * c->dc.H, B = 256;
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->d_scal + 2, 0, 8, c->stream));
+  map_count_kernel<<<div_up(npix, B), B, 0, c->stream>>>(npix, ms->m, ms->d_scal);
+  c->launches += 1;
+  return ESVO_OK;
+}
+int fuse_zero_fusion_counter(Ctx* c) {
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(c->map->d_scal, 0, 8, c->stream));
+  return ESVO_OK;
+}
+// D2H of the map scalars: out[0] = n_fusions since the last zeroing, out[2] = map size (after map_count)
+int fuse_fetch_scalars(Ctx* c, unsigned long long out[4]) {
+  MapState* ms = c->map;
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(ms->h_scal, ms->d_scal, 32, cudaMemcpyDeviceToHost, c->stream));
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 4; ++i) out[i] = ms->h_scal[i];
+  return ESVO_OK;
+}
+const double* fuse_frame_pose(Ctx* c) { return c->map->T_world_frame; }
+}  // namespace esvo

@@ -1,0 +1,327 @@
+// esvo_b200 product code -- time-surface raster (sm_100a).
+//
+// Replaces esvo_time_surface::TimeSurface::{eventsCallback, createTimeSurfaceAtTime} and
+// EventQueueMat (esvo_time_surface/src/TimeSurface.cpp:52-152,403-425, TimeSurface.h:28-96).
+//
+// Data layout (HBM, per camera): the event log is SoA (x u16 | y u16 | t i64 | pol u8) in push
+// order; the per-pixel deques of the reference are replaced by a "most recent event" index grid:
+//   cur_idx[y][x] = max{ i : event i landed on (x,y) }   (atomicMax over 64-bit global indices)
+// with its stamp/polarity cached beside it.  For a sync time T newer than every pushed stamp (the
+// normal case) this grid IS getMostRecentEventBeforeT.  For an older T the reference semantics are
+//   idx = max{ i : pix_i = pix, t_i < T }   valid iff  #{ j : pix_j = pix, t_j >= T } < queue_len
+// (events arrive time-ordered, so "t_i < T" is a prefix [0,k) of the log and the deque holds the
+// last queue_len arrivals); it is evaluated from the log on the general path below.
+// HBM-bound byte work: coalesced SoA reads, one scatter atomic per event, one fused
+// decay+convert+median pass over a shared-memory tile, one gather pass for the rectifying remap.
+#include "common.cuh"
+
+namespace esvo {
+
+// ---- push: scatter the new events into the incremental grids ----
+__global__ void ts_scatter_kernel(const uint16_t* __restrict__ ex, const uint16_t* __restrict__ ey,
+                                  const int64_t* __restrict__ et, size_t n, long long gbase, int W, int H,
+                                  long long* __restrict__ idx_grid, int32_t* __restrict__ scalars,
+                                  long long* __restrict__ max_t) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x = ex[i], y = ey[i];
+  long long t = et[i];
+  // time-ordered input is required (the reference's insertion sort makes out-of-order input
+  // re-insert the globally latest event instead, TimeSurface.cpp:421-422); flag violations.
+  if (i > 0 && et[i - 1] > t) scalars[1] = 1;
+  if (i == 0 && *max_t > t) scalars[1] = 1;
+  if (i == n - 1) atomicMax(max_t, t);
+  if (x >= W || y >= H) return;  // EventQueueMat::insideImage
+  atomicMax(&idx_grid[(size_t)y * W + x], gbase + (long long)i);
+}
+// second pass: the winner of each pixel caches its stamp and polarity
+__global__ void ts_scatter_fix_kernel(const uint16_t* __restrict__ ex, const uint16_t* __restrict__ ey,
+                                      const int64_t* __restrict__ et, const uint8_t* __restrict__ ep, size_t n,
+                                      long long gbase, int W, int H, const long long* __restrict__ idx_grid,
+                                      long long* __restrict__ t_grid, uint8_t* __restrict__ pol_grid) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x = ex[i], y = ey[i];
+  if (x >= W || y >= H) return;
+  size_t p = (size_t)y * W + x;
+  if (idx_grid[p] == gbase + (long long)i) { t_grid[p] = et[i]; pol_grid[p] = ep[i]; }
+}
+
+// ---- build, step 0: split position k = first log entry with t >= T; flag the general path ----
+__global__ void ts_split_kernel(const int64_t* __restrict__ et, size_t n, long long T, int32_t* scalars) {
+  size_t lo = 0, hi = n;
+  while (lo < hi) { size_t mid = (lo + hi) >> 1; if (et[mid] < T) lo = mid + 1; else hi = mid; }
+  scalars[0] = (int32_t)lo;
+  scalars[2] = (lo != n) ? 1 : 0;
+}
+// general path (no-ops when scalars[2]==0)
+__global__ void ts_general_init_kernel(const int32_t* __restrict__ scalars, size_t npix, const long long* __restrict__ bidx,
+                                       const long long* __restrict__ bt, const uint8_t* __restrict__ bpol,
+                                       long long* tidx, long long* tt, uint8_t* tpol, int32_t* cnt) {
+  if (!scalars[2]) return;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  tidx[i] = bidx[i]; tt[i] = bt[i]; tpol[i] = bpol[i]; cnt[i] = 0;
+}
+__global__ void ts_general_scatter_kernel(const int32_t* __restrict__ scalars, const uint16_t* __restrict__ ex,
+                                          const uint16_t* __restrict__ ey, size_t n, long long gbase, int W, int H,
+                                          long long* tidx, int32_t* cnt) {
+  if (!scalars[2]) return;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x = ex[i], y = ey[i];
+  if (x >= W || y >= H) return;
+  size_t p = (size_t)y * W + x;
+  if (i < (size_t)scalars[0]) atomicMax(&tidx[p], gbase + (long long)i);
+  else atomicAdd(&cnt[p], 1);
+}
+__global__ void ts_general_fix_kernel(const int32_t* __restrict__ scalars, const uint16_t* __restrict__ ex,
+                                      const uint16_t* __restrict__ ey, const int64_t* __restrict__ et,
+                                      const uint8_t* __restrict__ ep, size_t n, long long gbase, int W, int H,
+                                      const long long* tidx, long long* tt, uint8_t* tpol) {
+  if (!scalars[2]) return;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)scalars[0]) return;
+  int x = ex[i], y = ey[i];
+  if (x >= W || y >= H) return;
+  size_t p = (size_t)y * W + x;
+  if (tidx[p] == gbase + (long long)i) { tt[p] = et[i]; tpol[p] = ep[i]; }
+}
+
+// ---- build, step 1: decay + u8 convert + 3x3 median, fused over a shared-memory tile ----
+constexpr int TSX = 32, TSY = 8;
+__device__ __forceinline__ void sort2(int& a, int& b) { int lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+
+template <int KS>
+__global__ void ts_decay_median_kernel(const int32_t* __restrict__ scalars, const long long* __restrict__ cur_idx,
+                                       const long long* __restrict__ cur_t, const uint8_t* __restrict__ cur_pol,
+                                       const long long* __restrict__ tmp_idx, const long long* __restrict__ tmp_t,
+                                       const uint8_t* __restrict__ tmp_pol, const int32_t* __restrict__ cnt,
+                                       int queue_len, long long T, double decay_sec, int ignore_polarity, int W, int H,
+                                       int pitch, long long* __restrict__ out_idx, uint8_t* __restrict__ img) {
+  constexpr int R = KS / 2;
+  __shared__ uint8_t tile[TSY + 2 * R][TSX + 2 * R + 2];
+  const bool general = scalars[2] != 0;
+  const long long* gi = general ? tmp_idx : cur_idx;
+  const long long* gt = general ? tmp_t : cur_t;
+  const uint8_t* gp = general ? tmp_pol : cur_pol;
+  const int x0 = blockIdx.x * TSX, y0 = blockIdx.y * TSY;
+  for (int k = threadIdx.y * TSX + threadIdx.x; k < (TSY + 2 * R) * (TSX + 2 * R); k += TSX * TSY) {
+    int ty = k / (TSX + 2 * R), tx = k % (TSX + 2 * R);
+    int gx = min(max(x0 + tx - R, 0), W - 1), gy = min(max(y0 + ty - R, 0), H - 1);  // BORDER_REPLICATE
+    size_t p = (size_t)gy * W + gx;
+    long long idx = gi[p];
+    if (general && idx >= 0 && cnt[p] >= queue_len) idx = -1;   // fell out of the 20-deep queue
+    double v = 0.0;
+    long long ts = idx >= 0 ? gt[p] : 0;
+    if (idx >= 0 && !(ns_to_sec_dev(ts) > 0)) idx = -1;          // TimeSurface.cpp:73
+    if (idx >= 0) {
+      double dt = ns_to_sec_dev(T - ts);
+      v = exp(-dt / decay_sec);                                  // :77
+      if (!ignore_polarity) v *= gp[p] ? 1.0 : -1.0;
+    }
+    if (tx >= R && tx < TSX + R && ty >= R && ty < TSY + R && x0 + tx - R < W && y0 + ty - R < H)
+      out_idx[(size_t)(y0 + ty - R) * W + x0 + tx - R] = idx;
+    double s = ignore_polarity ? 255.0 * v : 255.0 * (v + 1.0) / 2.0;  // :123-126
+    int r = __double2int_rn(s);                                        // cvRound, half-to-even
+    tile[ty][tx] = (uint8_t)min(max(r, 0), 255);
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  int out;
+  if (KS == 1) out = tile[threadIdx.y][threadIdx.x];
+  else {
+    // 3x3 median by the classic 19-exchange network
+    int p0 = tile[threadIdx.y][threadIdx.x], p1 = tile[threadIdx.y][threadIdx.x + 1], p2 = tile[threadIdx.y][threadIdx.x + 2];
+    int p3 = tile[threadIdx.y + 1][threadIdx.x], p4 = tile[threadIdx.y + 1][threadIdx.x + 1], p5 = tile[threadIdx.y + 1][threadIdx.x + 2];
+    int p6 = tile[threadIdx.y + 2][threadIdx.x], p7 = tile[threadIdx.y + 2][threadIdx.x + 1], p8 = tile[threadIdx.y + 2][threadIdx.x + 2];
+    sort2(p1, p2); sort2(p4, p5); sort2(p7, p8); sort2(p0, p1); sort2(p3, p4); sort2(p6, p7);
+    sort2(p1, p2); sort2(p4, p5); sort2(p7, p8); sort2(p0, p3); sort2(p5, p8); sort2(p4, p7);
+    sort2(p3, p6); sort2(p1, p4); sort2(p2, p5); sort2(p4, p7); sort2(p4, p2); sort2(p6, p4);
+    sort2(p4, p2);
+    out = p4;
+  }
+  img[(size_t)y * pitch + x] = (uint8_t)out;
+}
+
+// ---- build, step 2: rectifying remap (cv::remap INTER_LINEAR, 1/32-px fixed point, border 0) ----
+__global__ void ts_remap_kernel(const uint8_t* __restrict__ src, const float* __restrict__ map1,
+                                const float* __restrict__ map2, int W, int H, int pitch, uint8_t* __restrict__ dst) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  size_t i = (size_t)y * W + x;
+  int sx = __float2int_rn(__fmul_rn(map1[i], 32.0f)), sy = __float2int_rn(__fmul_rn(map2[i], 32.0f));
+  int fx = sx & 31, fy = sy & 31;
+  int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767);
+  auto px = [&](int xx, int yy) -> int {
+    return (xx >= 0 && xx < W && yy >= 0 && yy < H) ? (int)src[(size_t)yy * pitch + xx] : 0;
+  };
+  int v = 32 * (32 - fx) * (32 - fy) * px(ix, iy) + 32 * fx * (32 - fy) * px(ix + 1, iy) +
+          32 * (32 - fx) * fy * px(ix, iy + 1) + 32 * fx * fy * px(ix + 1, iy + 1);
+  dst[(size_t)y * pitch + x] = (uint8_t)((v + (1 << 14)) >> 15);
+}
+__global__ void ts_copy_img_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+__global__ void fill_i64_kernel(long long* p, size_t n, long long v) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// --------------------------------------------------------------------------------------------
+template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+int ts_reset_state(Ctx* c, int cam) {
+  TsState& s = c->ts[cam];
+  const size_t npix = (size_t)c->dc.W * c->dc.H;
+  const int B = 256;
+  fill_i64_kernel<<<(unsigned)((npix + B - 1) / B), B, 0, c->stream>>>((long long*)s.cur_idx, npix, -1);
+  fill_i64_kernel<<<(unsigned)((npix + B - 1) / B), B, 0, c->stream>>>((long long*)s.base_idx, npix, -1);
+  c->launches += 2;
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(s.cur_t, 0, npix * 8, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(s.base_t, 0, npix * 8, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(s.cur_pol, 0, npix, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(s.base_pol, 0, npix, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(s.scalars, 0, 16 * sizeof(int32_t), c->stream));
+  long long mn = INT64_MIN;
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.max_t, &mn, 8, cudaMemcpyHostToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(s.img_out, 0, (size_t)c->dc.pitch * c->dc.H, c->stream));
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  s.log_n = 0; s.log_base = 0; s.built = false;
+  return ESVO_OK;
+}
+
+int ts_alloc(Ctx* c, int cam) {
+  TsState& s = c->ts[cam];
+  const size_t npix = (size_t)c->dc.W * c->dc.H;
+  s.log_cap = (size_t)1 << 22;  // 4 Mi events resident per camera (52 MiB); older ones fold into base grids
+  ESVO_CUDA_TRY(c, dmalloc(&s.ex, s.log_cap)); ESVO_CUDA_TRY(c, dmalloc(&s.ey, s.log_cap));
+  ESVO_CUDA_TRY(c, dmalloc(&s.et, s.log_cap)); ESVO_CUDA_TRY(c, dmalloc(&s.ep, s.log_cap));
+  ESVO_CUDA_TRY(c, dmalloc(&s.cur_idx, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.cur_t, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.cur_pol, npix));
+  ESVO_CUDA_TRY(c, dmalloc(&s.base_idx, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.base_t, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.base_pol, npix));
+  ESVO_CUDA_TRY(c, dmalloc(&s.tmp_idx, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.tmp_t, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.tmp_pol, npix));
+  ESVO_CUDA_TRY(c, dmalloc(&s.cnt, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.out_idx, npix));
+  ESVO_CUDA_TRY(c, dmalloc(&s.img_med, (size_t)c->dc.pitch * c->dc.H));
+  ESVO_CUDA_TRY(c, dmalloc(&s.img_out, (size_t)c->dc.pitch * c->dc.H));
+  ESVO_CUDA_TRY(c, dmalloc(&s.map1, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.map2, npix));
+  ESVO_CUDA_TRY(c, dmalloc(&s.scalars, 16)); ESVO_CUDA_TRY(c, dmalloc(&s.max_t, 1));
+  ESVO_CUDA_TRY(c, cudaMemcpy(s.map1, c->cam[cam].map1.data(), npix * 4, cudaMemcpyHostToDevice));
+  ESVO_CUDA_TRY(c, cudaMemcpy(s.map2, c->cam[cam].map2.data(), npix * 4, cudaMemcpyHostToDevice));
+  ESVO_CUDA_TRY(c, cudaMemset(s.img_med, 0, (size_t)c->dc.pitch * c->dc.H));
+  return ts_reset_state(c, cam);
+}
+void ts_free(Ctx* c, int cam) {
+  TsState& s = c->ts[cam];
+  void* ps[] = {s.ex, s.ey, s.et, s.ep, s.cur_idx, s.cur_t, s.cur_pol, s.base_idx, s.base_t, s.base_pol, s.tmp_idx,
+                s.tmp_t, s.tmp_pol, s.cnt, s.out_idx, s.img_med, s.img_out, s.map1, s.map2, s.scalars, s.max_t};
+  for (void* p : ps) if (p) cudaFree(p);
+  s = TsState();
+}
+
+// Evict the oldest half of the log into the base grids when the next push would overflow.
+static int ts_make_room(Ctx* c, int cam, size_t n_new) {
+  TsState& s = c->ts[cam];
+  if (n_new > s.log_cap) { c->set_error("event batch larger than the resident log"); return ESVO_ERR_CAPACITY; }
+  if (s.log_n + n_new <= s.log_cap) return ESVO_OK;
+  size_t drop = std::max(s.log_n / 2, s.log_n + n_new - s.log_cap);
+  const int B = 256;
+  unsigned g = (unsigned)((drop + B - 1) / B);
+  ts_scatter_kernel<<<g, B, 0, c->stream>>>(s.ex, s.ey, s.et, drop, s.log_base, c->dc.W, c->dc.H, (long long*)s.base_idx,
+                                            s.scalars + 8, (long long*)(s.max_t));
+  ts_scatter_fix_kernel<<<g, B, 0, c->stream>>>(s.ex, s.ey, s.et, s.ep, drop, s.log_base, c->dc.W, c->dc.H,
+                                                (const long long*)s.base_idx, (long long*)s.base_t, s.base_pol);
+  c->launches += 2;
+  size_t keep = s.log_n - drop;
+  // compaction through the (free) tail is not possible in place for overlapping ranges: stage via tmp copies
+  uint16_t* tx; uint16_t* ty; int64_t* tt; uint8_t* tp;
+  ESVO_CUDA_TRY(c, dmalloc(&tx, keep)); ESVO_CUDA_TRY(c, dmalloc(&ty, keep)); ESVO_CUDA_TRY(c, dmalloc(&tt, keep)); ESVO_CUDA_TRY(c, dmalloc(&tp, keep));
+  cudaMemcpyAsync(tx, s.ex + drop, keep * 2, cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(ty, s.ey + drop, keep * 2, cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(tt, s.et + drop, keep * 8, cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(tp, s.ep + drop, keep, cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(s.ex, tx, keep * 2, cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(s.ey, ty, keep * 2, cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(s.et, tt, keep * 8, cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(s.ep, tp, keep, cudaMemcpyDeviceToDevice, c->stream);
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaFree(tx); cudaFree(ty); cudaFree(tt); cudaFree(tp);
+  s.log_base += (int64_t)drop; s.log_n = keep;
+  return ESVO_OK;
+}
+
+// x/y/t/p are HOST pointers; the copies are enqueued on the ctx stream (pageable memory is staged
+// by the driver; callers that want true async overlap pass pinned buffers).
+int ts_push(Ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t, const uint8_t* p, size_t n) {
+  if (n == 0) return ESVO_OK;
+  TsState& s = c->ts[cam];
+  int rc = ts_make_room(c, cam, n);
+  if (rc) return rc;
+  size_t off = s.log_n;
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ex + off, x, n * 2, cudaMemcpyHostToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ey + off, y, n * 2, cudaMemcpyHostToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.et + off, t, n * 8, cudaMemcpyHostToDevice, c->stream));
+  if (p) ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ep + off, p, n, cudaMemcpyHostToDevice, c->stream));
+  else ESVO_CUDA_TRY(c, cudaMemsetAsync(s.ep + off, 1, n, c->stream));
+  const int B = 256;
+  unsigned g = (unsigned)((n + B - 1) / B);
+  long long gbase = s.log_base + (long long)off;
+  ts_scatter_kernel<<<g, B, 0, c->stream>>>(s.ex + off, s.ey + off, s.et + off, n, gbase, c->dc.W, c->dc.H,
+                                            (long long*)s.cur_idx, s.scalars, (long long*)s.max_t);
+  ts_scatter_fix_kernel<<<g, B, 0, c->stream>>>(s.ex + off, s.ey + off, s.et + off, s.ep + off, n, gbase, c->dc.W, c->dc.H,
+                                                (const long long*)s.cur_idx, (long long*)s.cur_t, s.cur_pol);
+  c->launches += 2;
+  s.log_n += n;
+  return ESVO_OK;
+}
+
+int ts_run_build(Ctx* c, int cam, int64_t T) {
+  TsState& s = c->ts[cam];
+  const DevConsts& d = c->dc;
+  const size_t npix = (size_t)d.W * d.H;
+  const int B = 256;
+  ts_split_kernel<<<1, 1, 0, c->stream>>>(s.et, s.log_n, T, s.scalars);
+  ts_general_init_kernel<<<(unsigned)((npix + B - 1) / B), B, 0, c->stream>>>(
+      s.scalars, npix, (const long long*)s.base_idx, (const long long*)s.base_t, s.base_pol, (long long*)s.tmp_idx,
+      (long long*)s.tmp_t, s.tmp_pol, s.cnt);
+  c->launches += 2;
+  if (s.log_n) {
+    unsigned g = (unsigned)((s.log_n + B - 1) / B);
+    ts_general_scatter_kernel<<<g, B, 0, c->stream>>>(s.scalars, s.ex, s.ey, s.log_n, s.log_base, d.W, d.H,
+                                                      (long long*)s.tmp_idx, s.cnt);
+    ts_general_fix_kernel<<<g, B, 0, c->stream>>>(s.scalars, s.ex, s.ey, s.et, s.ep, s.log_n, s.log_base, d.W, d.H,
+                                                  (const long long*)s.tmp_idx, (long long*)s.tmp_t, s.tmp_pol);
+    c->launches += 2;
+  }
+  dim3 blk(TSX, TSY), grd(div_up(d.W, TSX), div_up(d.H, TSY));
+  const double decay_sec = c->prm.decay_ms / 1000.0;
+  const bool backward = c->prm.time_surface_mode == ESVO_TS_BACKWARD;
+  uint8_t* med_dst = backward ? s.img_med : s.img_out;
+  const int ks = c->prm.median_blur_kernel_size > 0 ? 2 * c->prm.median_blur_kernel_size + 1 : 1;
+  if (ks == 3)
+    ts_decay_median_kernel<3><<<grd, blk, 0, c->stream>>>(
+        s.scalars, (const long long*)s.cur_idx, (const long long*)s.cur_t, s.cur_pol, (const long long*)s.tmp_idx,
+        (const long long*)s.tmp_t, s.tmp_pol, s.cnt, c->prm.max_event_queue_len, T, decay_sec, c->prm.ignore_polarity,
+        d.W, d.H, d.pitch, (long long*)s.out_idx, med_dst);
+  else if (ks == 1)
+    ts_decay_median_kernel<1><<<grd, blk, 0, c->stream>>>(
+        s.scalars, (const long long*)s.cur_idx, (const long long*)s.cur_t, s.cur_pol, (const long long*)s.tmp_idx,
+        (const long long*)s.tmp_t, s.tmp_pol, s.cnt, c->prm.max_event_queue_len, T, decay_sec, c->prm.ignore_polarity,
+        d.W, d.H, d.pitch, (long long*)s.out_idx, med_dst);
+  else { c->set_error("median_blur_kernel_size > 1 is not supported on the device path"); return ESVO_ERR_UNSUPPORTED; }
+  c->launches += 1;
+  if (backward) {
+    dim3 b2(32, 8), g2(div_up(d.W, 32), div_up(d.H, 8));
+    ts_remap_kernel<<<g2, b2, 0, c->stream>>>(s.img_med, s.map1, s.map2, d.W, d.H, d.pitch, s.img_out);
+    c->launches += 1;
+  } else {
+    c->set_error("FORWARD time-surface mode is not implemented on the device path yet");
+    return ESVO_ERR_UNSUPPORTED;
+  }
+  ESVO_CUDA_TRY(c, cudaGetLastError());
+  s.built = true;
+  return ESVO_OK;
+}
+
+}  // namespace esvo

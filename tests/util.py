@@ -1,0 +1,43 @@
+"""Shared helpers for the parity tests: one synthetic scenario, two backends fed identical inputs."""
+import functools
+
+import numpy as np
+
+from esvo_b200 import capi, configs, synth
+
+
+@functools.lru_cache(maxsize=8)
+def scenario(rig="hkust", seed=2, n_seeds=1500, t_ts=0.5):
+    kw = {}
+    if rig == "dsec":
+        kw = dict(n_segments=120)
+    return synth.make_stream(rig, seed=seed, n_seeds=n_seeds, t_ts=t_ts, **kw)
+
+
+def make_backends(rig, oracle_lib, product_lib, tweak=None):
+    l, r = configs.rig_calibs(rig)
+    po = configs.params_for(rig, oracle_lib)
+    pp = configs.params_for(rig, product_lib)
+    if tweak:
+        tweak(po); tweak(pp)
+    o = capi.Backend(oracle_lib, l, r, po)
+    g = capi.Backend(product_lib, l, r, pp)
+    # identical rectification tables on both sides (the product's own tables are checked separately)
+    for cam in (0, 1):
+        m1, m2, lut, mask = o.get_rectify_tables(cam)
+        g.set_rectify_tables(cam, m1, m2, lut, mask)
+    return o, g
+
+
+def build_ts_pair(b, s):
+    for cam, side in ((0, "left"), (1, "right")):
+        e = s[side]
+        b.ts_push_events(cam, e["x"], e["y"], e["t"], e["p"])
+    _, tl = b.ts_build(0, s["t_ts_ns"], want_idx=False)
+    _, tr = b.ts_build(1, s["t_ts_ns"], want_idx=False)
+    return tl, tr
+
+
+def rel(a, b):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
