@@ -29,8 +29,7 @@ __global__ void ts_scatter_kernel(const uint16_t* __restrict__ ex, const uint16_
   // time-ordered input is required (the reference's insertion sort makes out-of-order input
   // re-insert the globally latest event instead, TimeSurface.cpp:421-422); flag violations.
   if (i > 0 && et[i - 1] > t) scalars[1] = 1;
-  if (i == 0 && *max_t > t) scalars[1] = 1;
-  if (i == n - 1) atomicMax(max_t, t);
+  if (i == 0 && *max_t > t) scalars[1] = 1;   // max_t is advanced by the second pass, after this kernel
   if (x >= W || y >= H) return;  // EventQueueMat::insideImage
   atomicMax(&idx_grid[(size_t)y * W + x], gbase + (long long)i);
 }
@@ -38,9 +37,11 @@ __global__ void ts_scatter_kernel(const uint16_t* __restrict__ ex, const uint16_
 __global__ void ts_scatter_fix_kernel(const uint16_t* __restrict__ ex, const uint16_t* __restrict__ ey,
                                       const int64_t* __restrict__ et, const uint8_t* __restrict__ ep, size_t n,
                                       long long gbase, int W, int H, const long long* __restrict__ idx_grid,
-                                      long long* __restrict__ t_grid, uint8_t* __restrict__ pol_grid) {
+                                      long long* __restrict__ t_grid, uint8_t* __restrict__ pol_grid,
+                                      long long* __restrict__ max_t) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (i == n - 1 && max_t) atomicMax(max_t, (long long)et[i]);
   int x = ex[i], y = ey[i];
   if (x >= W || y >= H) return;
   size_t p = (size_t)y * W + x;
@@ -231,7 +232,7 @@ static int ts_make_room(Ctx* c, int cam, size_t n_new) {
   ts_scatter_kernel<<<g, B, 0, c->stream>>>(s.ex, s.ey, s.et, drop, s.log_base, c->dc.W, c->dc.H, (long long*)s.base_idx,
                                             s.scalars + 8, (long long*)(s.max_t));
   ts_scatter_fix_kernel<<<g, B, 0, c->stream>>>(s.ex, s.ey, s.et, s.ep, drop, s.log_base, c->dc.W, c->dc.H,
-                                                (const long long*)s.base_idx, (long long*)s.base_t, s.base_pol);
+                                                (const long long*)s.base_idx, (long long*)s.base_t, s.base_pol, nullptr);
   c->launches += 2;
   size_t keep = s.log_n - drop;
   // compaction through the (free) tail is not possible in place for overlapping ranges: stage via tmp copies
@@ -270,7 +271,7 @@ int ts_push(Ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t
   ts_scatter_kernel<<<g, B, 0, c->stream>>>(s.ex + off, s.ey + off, s.et + off, n, gbase, c->dc.W, c->dc.H,
                                             (long long*)s.cur_idx, s.scalars, (long long*)s.max_t);
   ts_scatter_fix_kernel<<<g, B, 0, c->stream>>>(s.ex + off, s.ey + off, s.et + off, s.ep + off, n, gbase, c->dc.W, c->dc.H,
-                                                (const long long*)s.cur_idx, (long long*)s.cur_t, s.cur_pol);
+                                                (const long long*)s.cur_idx, (long long*)s.cur_t, s.cur_pol, (long long*)s.max_t);
   c->launches += 2;
   s.log_n += n;
   return ESVO_OK;

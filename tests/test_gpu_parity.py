@@ -178,3 +178,62 @@ def test_mapping_at_time_multi_frame(oracle_lib, product_lib, rig):
         assert np.array_equal(mo["row"], mg["row"]) and np.array_equal(mo["col"], mg["col"])
         r = rel(mg["inv_depth"], mo["inv_depth"])
         assert (r < 1e-4).mean() > 0.995 and np.median(r) < 1e-9
+
+
+def _tracking_case(oracle_lib, product_lib, rig, analytical, perturb=True, seed=11):
+    s = scenario(rig)
+    o, g = make_backends(rig, oracle_lib, product_lib)
+    tl, _ = build_ts_pair(o, s)
+    rng = np.random.default_rng(seed)
+    # reference cloud: scene points visible from the current view, world frame, float32 like pcl::PointXYZ
+    pts = s["scene_points"]
+    Tw = s["T_world_left"]
+    pc = (pts - Tw[:3, 3]) @ Tw[:3, :3]
+    vis = pc[:, 2] > 0.1
+    sel = rng.choice(np.nonzero(vis)[0], size=min(6000, vis.sum()), replace=False)
+    cloud = pts[sel].astype(np.float32)
+    T_ref = Tw.copy()
+    T_prior = Tw.copy()
+    if perturb:
+        T_prior[:3, 3] += np.array([0.004, -0.003, 0.002]) * (1 if rig == "hkust" else 20)
+    res = []
+    for be in (o, g):
+        c = cloud.copy()
+        be.track_srand(1)
+        rc = be.track_reset(c, T_ref, T_prior, tl)
+        assert rc == 0
+        T, st = be.track_solve(analytical)
+        res.append((T, st, c))
+    return s, o, g, res
+
+
+@pytest.mark.parametrize("rig", ["hkust", "dsec"])
+def test_tracking_negative_ts_and_sampling_bit_exact(oracle_lib, product_lib, rig):
+    s, o, g, res = _tracking_case(oracle_lib, product_lib, rig, True)
+    no, ng = o.track_get_negative_ts(), g.track_get_negative_ts()
+    for a, b in zip(no, ng):
+        assert np.array_equal(a, b)
+    assert np.array_equal(res[0][2], res[1][2]), "rand()-driven partial shuffle differs"
+
+
+@pytest.mark.parametrize("rig,analytical", [("hkust", True), ("dsec", True), ("hkust", False)])
+def test_tracking_pose_parity(oracle_lib, product_lib, rig, analytical):
+    s, o, g, res = _tracking_case(oracle_lib, product_lib, rig, analytical)
+    (To, so, _), (Tg, sg, _) = res
+    print(rig, analytical, so, sg, "\n", To, "\n", Tg)
+    assert so["n_iter"] == sg["n_iter"] and so["n_points"] == sg["n_points"] and so["nfev"] == sg["nfev"]
+    assert np.abs(To[:3, :3] - Tg[:3, :3]).max() < 1e-4
+    tn = max(np.linalg.norm(To[:3, 3]), 1e-3)
+    assert np.linalg.norm(To[:3, 3] - Tg[:3, 3]) / tn < 1e-4
+    # and the tracker actually moved towards the true pose
+    Tw = s["T_world_left"]
+    assert np.linalg.norm(Tg[:3, 3] - Tw[:3, 3]) < np.linalg.norm(np.array([0.004, -0.003, 0.002]) * (1 if rig == "hkust" else 20))
+
+
+def test_tracking_too_few_points(oracle_lib, product_lib):
+    s = scenario("hkust")
+    o, g = make_backends("hkust", oracle_lib, product_lib)
+    tl, _ = build_ts_pair(o, s)
+    cloud = np.zeros((10, 3), np.float32); cloud[:, 2] = 1
+    for be in (o, g):
+        assert be.track_reset(cloud.copy(), np.eye(4), np.eye(4), tl) == 1
