@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ESVO mapping hot path on B200.
+
+Metric (BASELINE.json): depth-candidate patch evaluations / s (EventBM zncc_cost evaluations +
+DepthProblem::operator() evaluations actually executed) on BASELINE.json configs[1]:
+346x260 stereo time-surface pair + 5k DepthProblem seeds, one event stream per GPU (weak scaling).
+
+One "step" = one mapping frame of one stream, everything the reference does between two
+MappingAtTime calls: ingest the frame's raw events of both cameras (per-pixel most-recent-event
+grids), build both time surfaces at the frame stamp, hand them to the mapper, block-match the 5000
+newest left events, LM-refine the matches, cull, update the fusion window, fuse the whole window,
+clean, regularise.
+
+  value   : device-timed (CUDA events on the library's stream) with every input already resident
+            in HBM (esvo_*_dev entry points), max over ranks;
+  e2e     : the same step through the host-buffer C ABI from pinned host memory, H2D of the events /
+            seeds / poses and D2H of the counters and of the fused map inside the timed region;
+  --impl reference : the CPU restatement of the reference (oracle/, all host threads) on the same
+            workload -- the only legs where oracle/ is executed are this one and cpu_baseline.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BM_BYTES = 420.0          # 105 px x 4 B per BM candidate (f32 TS convention)
+LM_BYTES = 1024.0         # 2 x (15+1)(7+1) px x 4 B per LM residual evaluation
+N_SEEDS = 5000
+RIG = "hkust"
+FRAME_MS = 50.0           # mapping_rate_hz = 20
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop_evt, self.proc = gpu, [], threading.Event(), None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self._stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc:
+            self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(seed):
+    from esvo_b200 import synth
+    # one 50 ms mapping frame of the stream; the frame is replayed with shifted stamps every step
+    s = synth.make_stream(RIG, seed=seed, n_seeds=N_SEEDS, history_ms=FRAME_MS)
+    return s
+
+
+def shifted(s, k):
+    """Frame k of the synthetic stream = the base frame with all stamps advanced by k frame periods."""
+    dt = int(round(FRAME_MS * 1e6)) * k
+    out = {"t_ts_ns": s["t_ts_ns"] + dt, "T_world_left": s["T_world_left"], "poses": s["poses"],
+           "pose_t": s["pose_t"] + dt}
+    for side in ("left", "right"):
+        e = s[side]
+        out[side] = dict(x=e["x"], y=e["y"], t=e["t"] + dt, p=e["p"])
+    sd = s["seeds"]
+    out["seeds"] = dict(x=sd["x"], y=sd["y"], t=sd["t"] + dt)
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from esvo_b200 import capi, configs
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prod = capi.load_product()
+    l, r = configs.rig_calibs(RIG)
+    prm = configs.params_for(RIG, prod)
+    g = capi.Backend(prod, l, r, prm, device=local_rank)
+    base = make_workload(seed=10 + rank)
+    K, Wm = args.steps, args.warmup
+    frames = [shifted(base, k) for k in range(2 * (K + Wm) + 2)]
+    stream = torch.cuda.ExternalStream(g.stream(), device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+    # ---------------- leg 1: inputs resident in HBM ----------------
+    dframes = []
+    for f in frames[: K + Wm]:
+        d = {side: {k: dev(v) for k, v in f[side].items()} for side in ("left", "right")}
+        d["seeds"] = {k: dev(v) for k, v in f["seeds"].items()}
+        d["pose_t"] = dev(f["pose_t"]); d["poses"] = dev(f["poses"])
+        dframes.append(d)
+    torch.cuda.synchronize()
+    u16, i64, u8, f64 = C.POINTER(C.c_uint16), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_double)
+
+    def P(t, ty):
+        return C.cast(t.data_ptr(), ty)
+
+    def step_resident(f, d):
+        for cam, side in ((0, "left"), (1, "right")):
+            e = d[side]
+            g._call("ts_push_events_dev", [C.c_int, u16, u16, i64, u8, C.c_size_t], cam, P(e["x"], u16), P(e["y"], u16),
+                    P(e["t"], i64), P(e["p"], u8), e["x"].numel())
+            g.run_ts_build(cam, f["t_ts_ns"])
+        T = np.ascontiguousarray(f["T_world_left"], np.float64)
+        g._call("set_ts_pair_dev", [f64], T.ctypes.data_as(f64))
+        sd = d["seeds"]
+        g._call("stage_mapping_inputs_dev", [u16, u16, i64, C.c_size_t, i64, f64, C.c_size_t], P(sd["x"], u16), P(sd["y"], u16),
+                P(sd["t"], i64), sd["x"].numel(), P(d["pose_t"], i64), P(d["poses"], f64), d["pose_t"].numel())
+        g.run_mapping()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for k in range(Wm):
+            step_resident(frames[k], dframes[k])
+        g.sync()
+        ctr = g.fetch_mapping_counters()
+        g._call("profile", [C.c_int], 1)
+        g._call("profile_read", [f64, C.POINTER(C.c_uint64)], (C.c_double * 8)(), (C.c_uint64 * 8)())
+        sampler = ClockSampler(local_rank); sampler.start()
+        time.sleep(0.3)
+        barrier()
+        launches0 = g.launch_count()
+        evs = []
+        t_wall0 = time.perf_counter()
+        for k in range(Wm, Wm + K):
+            flush.fill_(k & 255)                       # L2 flush between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_resident(frames[k], dframes[k])
+            e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = g.launch_count() - launches0
+        clocks = sampler.stop()
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        ms = (C.c_double * 8)(); cnt = (C.c_uint64 * 8)()
+        g._call("profile_read", [f64, C.POINTER(C.c_uint64)], ms, cnt)
+        g._call("profile", [C.c_int], 0)
+        ctr = g.fetch_mapping_counters()
+    total_ms = float(np.sum(step_ms))
+    evals_ref_equiv = ctr["bm_evals"] + ctr["lm_evals"]
+    # executed LM evaluations (the kernel re-uses f(x) inside the forward difference instead of recomputing it)
+    dbg = g.L.lib.esvo_debug_counter
+    dbg.argtypes = [C.c_void_p, C.c_int]; dbg.restype = C.c_uint64
+    lm_exec = int(dbg(g.ctx, 7))
+    evals_step = ctr["bm_evals"] + lm_exec
+    # ---------------- leg 2: end to end through the host-buffer C ABI ----------------
+    pinned = []
+    for f in frames[K + Wm: 2 * (K + Wm)]:
+        pf = dict(f)
+        for side in ("left", "right"):
+            pf[side] = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in f[side].items()}
+        pf["seeds"] = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in f["seeds"].items()}
+        pf["pose_t"] = torch.from_numpy(np.ascontiguousarray(f["pose_t"])).pin_memory().numpy()
+        pf["poses"] = torch.from_numpy(np.ascontiguousarray(f["poses"])).pin_memory().numpy()
+        pinned.append(pf)
+    h2d = d2h = 0
+
+    def step_e2e(f):
+        nonlocal h2d, d2h
+        for cam, side in ((0, "left"), (1, "right")):
+            e = f[side]
+            g.stage_ts_events(cam, e["x"], e["y"], e["t"], e["p"])
+            g.run_ts_build(cam, f["t_ts_ns"])
+            h2d += e["x"].size * 13
+        T = np.ascontiguousarray(f["T_world_left"], np.float64)
+        g._call("set_ts_pair_dev", [f64], T.ctypes.data_as(f64))
+        sd = f["seeds"]
+        c = g.mapping_at_time(sd["x"], sd["y"], sd["t"], f["pose_t"], f["poses"])
+        m = g.map_download()
+        h2d += sd["x"].size * 12 + f["pose_t"].size * 136 + 128
+        d2h += 64 + 32 + m.nbytes + m.size * 8
+        return c
+
+    for f in pinned[:Wm]:
+        step_e2e(f)
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for f in pinned[Wm: Wm + K]:
+        ce = step_e2e(f)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_evals = ce["bm_evals"] + ce["lm_evals"]
+    # TS-only rate (second half of the metric): resident events -> rectified u8 TS, both cameras per step
+    ts_frames_per_s = 2 * K / (ms[0] / 1e3) if ms[0] > 0 else None
+
+    # max over ranks
+    tot = torch.tensor([total_ms, e2e_s * 1e3, float(evals_step), float(e2e_evals)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms = float(mx[0]), float(mx[1])
+        evals_all, e2e_evals_all = float(sm[2]), float(sm[3])
+    else:
+        e2e_ms = e2e_s * 1e3
+        evals_all, e2e_evals_all = float(evals_step), float(e2e_evals)
+    if rank != 0:
+        return
+    peak, peak_kind = load_peaks()
+    value = evals_all * K / (total_ms / 1e3)
+    e2e_value = e2e_evals_all * K / (e2e_ms / 1e3)
+    # roofline of the dominant kernel of the step
+    bm_ms, lm_ms = ms[1] / max(cnt[1], 1), ms[3] / max(cnt[3], 1)
+    ncand = ctr["bm_evals"] / max(ctr["n_events"], 1)
+    bm_bytes = ctr["bm_evals"] * BM_BYTES * (1 + 1 / max(ncand, 1))
+    lm_bytes = lm_exec * LM_BYTES
+    bm_roof = {"kernel": "bm_kernel", "bound": "hbm", "achieved": bm_bytes / (bm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+               "ms_per_launch": bm_ms, "algorithmic_bytes_per_launch": bm_bytes, "traffic": None}
+    lm_roof = {"kernel": "lm_kernel", "bound": "hbm", "achieved": lm_bytes / (lm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+               "ms_per_launch": lm_ms, "algorithmic_bytes_per_launch": lm_bytes, "traffic": None}
+    for rf in (bm_roof, lm_roof):
+        rf["frac"] = rf["achieved"] / peak
+        rf["peak_kind"] = peak_kind
+    dom, other = (lm_roof, bm_roof) if lm_ms >= bm_ms else (bm_roof, lm_roof)
+    out = {
+        "metric": "depth-candidate patch evals/s (EventBM zncc + DepthProblem LM) @346x260, 5k seeds/frame",
+        "value": value, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 (LM/fusion/tracking), u8/int32 exact (TS, BM moments)", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: 346x260 stereo TS pair + 5k DepthProblem seeds per frame (hkust rig, "
+                               "mapping_hkust.yaml), one event stream per GPU; step = event ingest + 2 TS builds + BM + LM + cull + "
+                               "20-frame window fusion + clean + regularise",
+                   "seeds_per_frame": N_SEEDS, "events_per_frame_per_camera": int(base["left"]["x"].size),
+                   "parallelism": f"{world} independent streams, one per GPU, no data-path collective",
+                   "l2": "256 MiB write between timed steps (excluded from the per-step CUDA-event timing)"},
+        "e2e": {"value": e2e_value, "unit": "evals/s", "ms_per_step": e2e_ms / K, "h2d_bytes_per_step": h2d // K,
+                "d2h_bytes_per_step": d2h // K},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": dom, "roofline_other": other,
+        "ts_frames_per_s": ts_frames_per_s,
+        "breakdown_ms_per_step": {"time_surface_x2": ms[0] / K, "block_matching": ms[1] / K, "seed_order": ms[2] / K,
+                                  "depth_lm": ms[3] / K, "point_order_cull": ms[4] / K, "fusion_clean_regularise": ms[5] / K},
+        "per_step": {"bm_evals": ctr["bm_evals"], "lm_evals_reference_equivalent": ctr["lm_evals"], "lm_evals_executed": lm_exec,
+                     "n_seeds": ctr["n_seeds"], "n_solved": ctr["n_solved"], "n_culled": ctr["n_culled"],
+                     "n_fusions": ctr["n_fusions"], "map_size": ctr["map_size"]},
+        "wall_s_timed_region": t_wall,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_leg(base, sample_steps=3)
+    print(json.dumps(out))
+
+
+def cpu_leg(base, sample_steps, threads=None):
+    """The oracle (a port of the reference CPU path) on the host cores: bounded sample of the same workload."""
+    from esvo_b200 import capi, configs
+    orc = capi.load_oracle()
+    l, r = configs.rig_calibs(RIG)
+    o = capi.Backend(orc, l, r, configs.params_for(RIG, orc))
+    nthreads = threads or (os.cpu_count() or 1)
+    orc.lib.esvo_oracle_set_exec_threads(o.ctx, C.c_int(nthreads))
+    evals = 0
+    ts_s = map_s = 0.0
+    t0 = time.perf_counter()
+    for k in range(sample_steps):
+        f = shifted(base, k)
+        ta = time.perf_counter()
+        for cam, side in ((0, "left"), (1, "right")):
+            e = f[side]
+            o.ts_push_events(cam, e["x"], e["y"], e["t"], e["p"])
+            o.ts_build(cam, f["t_ts_ns"], want_idx=False, want_ts=False)
+        tb = time.perf_counter()
+        o.set_ts_pair(None, None, f["T_world_left"])
+        sd = f["seeds"]
+        c = o.mapping_at_time(sd["x"], sd["y"], sd["t"], f["pose_t"], f["poses"])
+        tc = time.perf_counter()
+        ts_s += tb - ta; map_s += tc - tb
+        evals += c["bm_evals"] + c["lm_evals"]
+    dt = time.perf_counter() - t0
+    return {"value": evals / dt, "unit": "evals/s", "cores": nthreads, "kind": "port",
+            "sample": f"{sample_steps} mapping frames of the same workload (event ingest + 2 TS builds single-threaded like "
+                      f"NUM_THREAD_TS=1; BM+LM on {nthreads} threads with the reference's interleaved fan-out; fusion single-threaded)",
+            "ms_per_step": dt / sample_steps * 1e3, "ts_ms_per_step": ts_s / sample_steps * 1e3,
+            "mapping_ms_per_step": map_s / sample_steps * 1e3}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    base = make_workload(seed=10)
+    K, Wm = args.steps, args.warmup
+    cpu_leg(base, sample_steps=max(1, min(Wm, 2)))
+    leg = cpu_leg(base, sample_steps=K)
+    out = {"impl": "reference",
+           "metric": "depth-candidate patch evals/s (EventBM zncc + DepthProblem LM) @346x260, 5k seeds/frame",
+           "value": leg["value"], "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": leg["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[1]: 346x260 stereo TS pair + 5k DepthProblem seeds per frame (hkust rig), "
+                                  "CPU restatement of the reference (oracle/; the reference itself needs ROS/Eigen/OpenCV C++ and "
+                                  "cannot be built here), one stream on rank 0"},
+           "cpu_baseline": leg,
+           "e2e": {"value": leg["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -168,7 +168,8 @@ ESVO_API esvo_ctx* esvo_create(int device, const esvo_calib* left, const esvo_ca
   const size_t npix = (size_t)d.W * d.H, nimg = (size_t)d.pitch * d.H;
   if (dmalloc(&c->d_lut, 2 * npix) || dmalloc(&c->d_mask, npix) || dmalloc(&c->obs_l, nimg) || dmalloc(&c->obs_r, nimg) ||
       dmalloc(&c->obs_ls, nimg) || dmalloc(&c->obs_rs, nimg) || dmalloc(&c->d_T_left_world, 16) ||
-      dmalloc(&c->d_counters, kCounters) || cudaMallocHost((void**)&c->h_counters, kCounters * 8))
+      dmalloc(&c->d_counters, kCounters) || cudaMallocHost((void**)&c->h_counters, kCounters * 8) ||
+      cudaMallocHost((void**)&c->h_pin, 64 * 8))
     return bail(ESVO_ERR_CUDA);
   cudaMemset(c->d_counters, 0, kCounters * 8);
   cudaMemset(c->obs_l, 0, nimg); cudaMemset(c->obs_r, 0, nimg); cudaMemset(c->obs_ls, 0, nimg); cudaMemset(c->obs_rs, 0, nimg);
@@ -195,6 +196,8 @@ ESVO_API void esvo_destroy(esvo_ctx* c) {
   for (auto& f : c->win) { cudaFree(f.pts); cudaFree(f.cnt); }
   for (auto& f : c->win_pool) { cudaFree(f.pts); cudaFree(f.cnt); }
   if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  for (auto e : c->prof_pool) cudaEventDestroy(e);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -233,7 +236,13 @@ ESVO_API int esvo_stage_ts_events(esvo_ctx* c, int cam, const uint16_t* x, const
                                   const uint8_t* pol, size_t n) {
   CHECK_CTX(c);
   if (cam < 0 || cam > 1 || (n && (!x || !y || !t))) return ESVO_ERR_INVALID_ARG;
-  return ts_push(c, cam, x, y, t, pol, n);
+  return ts_push(c, cam, x, y, t, pol, n, false);
+}
+ESVO_API int esvo_ts_push_events_dev(esvo_ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t,
+                                     const uint8_t* pol, size_t n) {
+  CHECK_CTX(c);
+  if (cam < 0 || cam > 1 || (n && (!x || !y || !t))) return ESVO_ERR_INVALID_ARG;
+  return ts_push(c, cam, x, y, t, pol, n, true);
 }
 ESVO_API int esvo_ts_push_events(esvo_ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t,
                                  const uint8_t* pol, size_t n) {
@@ -291,6 +300,25 @@ ESVO_API int esvo_set_ts_pair(esvo_ctx* c, const uint8_t* l, const uint8_t* r, c
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_ls, c->obs_l, nimg, cudaMemcpyDeviceToDevice, c->stream));
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_rs, c->obs_r, nimg, cudaMemcpyDeviceToDevice, c->stream));
   ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // Ti and the caller's images are host stack/heap
+  c->obs_set = true;
+  return ESVO_OK;
+}
+
+ESVO_API int esvo_set_ts_pair_dev(esvo_ctx* c, const double T[16]) {
+  CHECK_CTX(c);
+  if (!T) return ESVO_ERR_INVALID_ARG;
+  if (!c->ts[0].built || !c->ts[1].built) { c->set_error("esvo_set_ts_pair_dev needs a built time surface for both cameras"); return ESVO_ERR_STATE; }
+  const size_t nimg = (size_t)c->dc.pitch * c->dc.H;
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_l, c->ts[0].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_r, c->ts[1].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_ls, c->ts[0].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_rs, c->ts[1].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  std::memcpy(c->T_world_left, T, sizeof(c->T_world_left));
+  // the pinned block may still be in flight from the previous frame: double buffer by parity
+  static thread_local int flip = 0;
+  double* Ti = c->h_pin + 16 * (flip++ & 1);
+  rigid_inverse(T, Ti);
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_T_left_world, Ti, 128, cudaMemcpyHostToDevice, c->stream));
   c->obs_set = true;
   return ESVO_OK;
 }

@@ -7,6 +7,7 @@
 namespace esvo {
 int fuse_zero_fusion_counter(Ctx* c);
 int fuse_fetch_scalars(Ctx* c, unsigned long long out[4]);
+int fuse_reserve(Ctx* c, size_t total_points);
 
 template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
 
@@ -30,17 +31,23 @@ static int fetch_counters2(Ctx* c) {
 static int run_mapping_frame(Ctx* c) {
   const esvo_params& p = c->prm;
   int rc;
+  cudaEvent_t pe = c->prof_begin(1);
   if (p.smooth_time_surface && (rc = smooth_obs(c))) return rc;           // createMatchProblem (EventBM.cpp:68-72)
   ESVO_CUDA_TRY(c, cudaMemsetAsync(c->d_counters, 0, kCounters * 8, c->stream));
   if ((rc = bm_run(c))) return rc;                                        // :308-309
+  c->prof_end(pe); pe = c->prof_begin(2);
   if ((rc = seeds_order(c))) return rc;
+  c->prof_end(pe); pe = c->prof_begin(3);
   if ((rc = lm_run(c, c->d_seeds, 0))) return rc;                         // :330
+  c->prof_end(pe);
   Ctx::WinFrame f;
   if ((rc = win_acquire(c, std::max<size_t>(c->n_ev, 1), f))) return rc;
   const double cost_thr = p.residual_vis_threshold * p.residual_vis_threshold * (double)(p.patch_size_x * p.patch_size_y);
+  pe = c->prof_begin(4);
   if ((rc = points_order_impl(c, c->d_seeds, 0, 1, p.stdvar_vis_threshold, cost_thr, p.invdepth_min_range,
                               p.invdepth_max_range, f.pts, f.cnt)))       // :334 pointCulling
     return rc;
+  c->prof_end(pe);
   c->win.push_back(f);                                                    // :342-368
   if (p.fusion_strategy == ESVO_FUSION_CONST_POINTS) {
     // needs the per-frame counts on the host: one small D2H per frame (the reference's CONST_FRAMES cfgs avoid it)
@@ -63,8 +70,10 @@ static int run_mapping_frame(Ctx* c) {
   } else {
     while (c->win.size() > (size_t)p.max_num_fusion_frames) { c->win_pool.push_back(c->win.front()); c->win.erase(c->win.begin()); }
   }
+  pe = c->prof_begin(5);
   if ((rc = fuse_reset_map(c, c->T_world_left))) return rc;               // :268-272 fresh DepthFrame at the obs pose
   if ((rc = fuse_zero_fusion_counter(c))) return rc;
+  { size_t tot = 0; for (auto& w : c->win) tot += w.cap; if ((rc = fuse_reserve(c, tot))) return rc; }
   for (auto it = c->win.rbegin(); it != c->win.rend(); ++it)              // :372-377 newest first
     if ((rc = fuse_points(c, it->pts, it->cap, (const uint64_t*)it->cnt, p.fusion_radius, 0))) return rc;
   if ((rc = fuse_finish(c))) return rc;
@@ -73,7 +82,9 @@ static int run_mapping_frame(Ctx* c) {
                         p.invdepth_min_range)))
       return rc;
   if (p.regularization && (rc = map_regularize(c))) return rc;            // :390-395
-  return map_count(c);
+  rc = map_count(c);
+  c->prof_end(pe);
+  return rc;
 }
 
 static int fetch_mapping_counters(Ctx* c, uint64_t out[8]) {
@@ -167,6 +178,43 @@ ESVO_API int esvo_stage_mapping_inputs(esvo_ctx* c, const uint16_t* ex, const ui
   if (np) {
     ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_pose_t, pt, np * 8, cudaMemcpyHostToDevice, c->stream));
     ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_poses, poses, np * 16 * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  return ESVO_OK;
+}
+ESVO_API int esvo_stage_mapping_inputs_dev(esvo_ctx* c, const uint16_t* ex, const uint16_t* ey, const int64_t* et, size_t n,
+                                           const int64_t* pt, const double* poses, size_t np) {
+  CHECK_CTX(c);
+  if (n && (!ex || !ey || !et)) return ESVO_ERR_INVALID_ARG;
+  if (np && (!pt || !poses)) return ESVO_ERR_INVALID_ARG;
+  int rc = map_alloc_inputs(c, n, np);
+  if (rc) return rc;
+  c->n_ev = n; c->n_poses = np;
+  if (n) {
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ex, ex, n * 2, cudaMemcpyDeviceToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ey, ey, n * 2, cudaMemcpyDeviceToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_et, et, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (np) {
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_pose_t, pt, np * 8, cudaMemcpyDeviceToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_poses, poses, np * 16 * 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return ESVO_OK;
+}
+ESVO_API uint64_t esvo_debug_counter(esvo_ctx* c, int idx) { return (c && idx >= 0 && idx < kCounters) ? c->h_counters[idx] : 0; }
+ESVO_API int esvo_profile(esvo_ctx* c, int enable) { CHECK_CTX(c); c->prof = enable != 0; return ESVO_OK; }
+ESVO_API int esvo_profile_read(esvo_ctx* c, double ms[8], uint64_t cnt[8]) {
+  CHECK_CTX(c);
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int s = 0; s < 8; ++s) {
+    double tot = 0;
+    for (auto& pr : c->prof_ev[s]) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) tot += t;
+      c->prof_pool.push_back(pr.first); c->prof_pool.push_back(pr.second);
+    }
+    if (ms) ms[s] = tot;
+    if (cnt) cnt[s] = c->prof_ev[s].size();
+    c->prof_ev[s].clear();
   }
   return ESVO_OK;
 }

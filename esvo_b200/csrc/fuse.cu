@@ -476,5 +476,6 @@ int fuse_fetch_scalars(Ctx* c, unsigned long long out[4]) {
   for (int i = 0; i < 4; ++i) out[i] = ms->h_scal[i];
   return ESVO_OK;
 }
+int fuse_reserve(Ctx* c, size_t total_points) { return prop_reserve(c, total_points); }
 const double* fuse_frame_pose(Ctx* c) { return c->map->T_world_frame; }
 }  // namespace esvo

@@ -254,16 +254,18 @@ static int ts_make_room(Ctx* c, int cam, size_t n_new) {
 
 // x/y/t/p are HOST pointers; the copies are enqueued on the ctx stream (pageable memory is staged
 // by the driver; callers that want true async overlap pass pinned buffers).
-int ts_push(Ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t, const uint8_t* p, size_t n) {
+int ts_push(Ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t, const uint8_t* p, size_t n, bool dev_src) {
   if (n == 0) return ESVO_OK;
   TsState& s = c->ts[cam];
   int rc = ts_make_room(c, cam, n);
   if (rc) return rc;
   size_t off = s.log_n;
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ex + off, x, n * 2, cudaMemcpyHostToDevice, c->stream));
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ey + off, y, n * 2, cudaMemcpyHostToDevice, c->stream));
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.et + off, t, n * 8, cudaMemcpyHostToDevice, c->stream));
-  if (p) ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ep + off, p, n, cudaMemcpyHostToDevice, c->stream));
+  const cudaMemcpyKind kind = dev_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  cudaEvent_t pe = c->prof_begin(0);
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ex + off, x, n * 2, kind, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ey + off, y, n * 2, kind, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.et + off, t, n * 8, kind, c->stream));
+  if (p) ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ep + off, p, n, kind, c->stream));
   else ESVO_CUDA_TRY(c, cudaMemsetAsync(s.ep + off, 1, n, c->stream));
   const int B = 256;
   unsigned g = (unsigned)((n + B - 1) / B);
@@ -273,6 +275,7 @@ int ts_push(Ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t
   ts_scatter_fix_kernel<<<g, B, 0, c->stream>>>(s.ex + off, s.ey + off, s.et + off, s.ep + off, n, gbase, c->dc.W, c->dc.H,
                                                 (const long long*)s.cur_idx, (long long*)s.cur_t, s.cur_pol, (long long*)s.max_t);
   c->launches += 2;
+  c->prof_end(pe);
   s.log_n += n;
   return ESVO_OK;
 }
@@ -282,6 +285,7 @@ int ts_run_build(Ctx* c, int cam, int64_t T) {
   const DevConsts& d = c->dc;
   const size_t npix = (size_t)d.W * d.H;
   const int B = 256;
+  cudaEvent_t pe = c->prof_begin(0);
   ts_split_kernel<<<1, 1, 0, c->stream>>>(s.et, s.log_n, T, s.scalars);
   ts_general_init_kernel<<<(unsigned)((npix + B - 1) / B), B, 0, c->stream>>>(
       s.scalars, npix, (const long long*)s.base_idx, (const long long*)s.base_t, s.base_pol, (long long*)s.tmp_idx,
@@ -320,6 +324,7 @@ int ts_run_build(Ctx* c, int cam, int64_t T) {
     c->set_error("FORWARD time-surface mode is not implemented on the device path yet");
     return ESVO_ERR_UNSUPPORTED;
   }
+  c->prof_end(pe);
   ESVO_CUDA_TRY(c, cudaGetLastError());
   s.built = true;
   return ESVO_OK;

@@ -264,6 +264,26 @@ ESVO_API int esvo_stage_mapping_inputs(esvo_ctx* ctx, const uint16_t* ex, const 
 ESVO_API int esvo_run_mapping(esvo_ctx* ctx);
 ESVO_API int esvo_fetch_mapping_counters(esvo_ctx* ctx, uint64_t counters_out[8]);
 ESVO_API int esvo_sync(esvo_ctx* ctx);
+/* Device-pointer forms (suffix _dev): the arrays are CUDA device pointers on the ctx's device, i.e.
+ * the inputs are already resident in HBM; work is enqueued on the ctx stream, nothing is synchronised.
+ * esvo_set_ts_pair_dev hands the images of the last two esvo_run_ts_build calls to the mapper. */
+ESVO_API int esvo_ts_push_events_dev(esvo_ctx* ctx, int cam, const uint16_t* x_dev, const uint16_t* y_dev,
+                                     const int64_t* t_ns_dev, const uint8_t* pol_dev, size_t n);
+ESVO_API int esvo_stage_mapping_inputs_dev(esvo_ctx* ctx, const uint16_t* ex_dev, const uint16_t* ey_dev,
+                                           const int64_t* et_ns_dev, size_t n_events,
+                                           const int64_t* pose_t_ns_dev, const double* poses_dev,
+                                           size_t n_poses);
+ESVO_API int esvo_set_ts_pair_dev(esvo_ctx* ctx, const double T_world_left[16]);
+/* Per-stage device timing with CUDA events on the ctx stream.  Stages: 0 time surface, 1 block
+ * matching, 2 seed ordering, 3 depth LM, 4 point ordering/culling, 5 fusion+clean+regularise,
+ * 6 tracking.  esvo_profile_read synchronises, returns accumulated ms and launch counts per stage
+ * since the last read and clears them. */
+/* Raw device counters of the last esvo_fetch_mapping_counters / esvo_mapping_at_time
+ * (idx 7 = DepthProblem evaluations actually executed by the LM kernel, which re-uses f(x) inside
+ * the forward difference instead of recomputing it like NumericalDiff does). */
+ESVO_API uint64_t esvo_debug_counter(esvo_ctx* ctx, int idx);
+ESVO_API int esvo_profile(esvo_ctx* ctx, int enable);
+ESVO_API int esvo_profile_read(esvo_ctx* ctx, double ms_out[8], uint64_t count_out[8]);
 /* CUDA stream of the ctx (cudaStream_t as void*), so callers can record events on it. */
 ESVO_API void* esvo_stream(esvo_ctx* ctx);
 /* Number of kernel launches issued by this ctx so far. */

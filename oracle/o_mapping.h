@@ -6,6 +6,7 @@
 #pragma once
 #include <deque>
 #include <map>
+#include <thread>
 
 #include "eigen_lm.h"
 #include "o_core.h"
@@ -202,9 +203,12 @@ struct EventBM {
   }
   // zncc_cost (EventBM.cpp:317-333)
   static double zncc_cost(const double* l, const double* r, size_t n) {
-    std::vector<double> ln(n), rn(n);
-    normalizePatch(l, ln.data(), n);
-    normalizePatch(r, rn.data(), n);
+    double sl[256], sr[256];   // stack scratch for the usual 15x7 patch; heap only for larger ones
+    std::vector<double> hl, hr;
+    double *ln = sl, *rn = sr;
+    if (n > 256) { hl.resize(n); hr.resize(n); ln = hl.data(); rn = hr.data(); }
+    normalizePatch(l, ln, n);
+    normalizePatch(r, rn, n);
     double s = 0;
     for (size_t i = 0; i < n; ++i) s += ln[i] * rn[i];
     return 0.5 * (1 - s / n);
@@ -295,15 +299,35 @@ struct EventBM {
     return false;
   }
   // match_all_HyperThread (:269-315): NT interleaved jobs, results concatenated per thread.
+  // exec_threads > 1 only changes how the work is executed (timing legs); the output is always
+  // assembled in the reference's NT-interleaved thread-major order.
   void match_all(const uint16_t* ex, const uint16_t* ey, const int64_t* et, size_t n,
                  const int64_t* pose_t, const double* poses, size_t n_poses, int NT,
-                 std::vector<Seed>& vEMP) {
+                 std::vector<Seed>& vEMP, int exec_threads = 1) {
     vEMP.clear(); n_evals = 0;
+    if (exec_threads <= 1) {
+      for (int tid = 0; tid < NT; ++tid)
+        for (size_t i = tid; i < n; i += NT) {
+          Seed em;
+          if (match_an_event(ex[i], ey[i], et[i], pose_t, poses, n_poses, em)) vEMP.push_back(em);
+        }
+      return;
+    }
+    std::vector<Seed> dense(n);
+    std::vector<char> flag(n, 0);
+    std::vector<uint64_t> ev(exec_threads, 0);
+    std::vector<std::thread> th;
+    for (int w = 0; w < exec_threads; ++w)
+      th.emplace_back([&, w]() {
+        EventBM me = *this;
+        me.n_evals = 0;
+        for (size_t i = w; i < n; i += exec_threads) flag[i] = me.match_an_event(ex[i], ey[i], et[i], pose_t, poses, n_poses, dense[i]);
+        ev[w] = me.n_evals;
+      });
+    for (auto& t : th) t.join();
+    for (auto e : ev) n_evals += e;
     for (int tid = 0; tid < NT; ++tid)
-      for (size_t i = tid; i < n; i += NT) {
-        Seed em;
-        if (match_an_event(ex[i], ey[i], et[i], pose_t, poses, n_poses, em)) vEMP.push_back(em);
-      }
+      for (size_t i = tid; i < n; i += NT) if (flag[i]) vEMP.push_back(dense[i]);
   }
 };
 
@@ -361,9 +385,12 @@ struct DepthProblem {
     const int N = wx * wy;
     double x1[2], x2[2];
     if (!warping(rho, x1, x2)) { fill_invalid(fvec); return 0; }
-    std::vector<double> tau1(N), tau2(N);
-    if (patchInterpolation(obs->TS_left.data(), obs->W, obs->H, x1, wx, wy, tau1.data()) &&
-        patchInterpolation(obs->TS_right.data(), obs->W, obs->H, x2, wx, wy, tau2.data())) {
+    double st1[256], st2[256], sR[256], sR2[256];
+    std::vector<double> h1, h2, h3, h4;
+    double *tau1 = st1, *tau2 = st2, *vR = sR, *vR2 = sR2;
+    if (N > 256) { h1.resize(N); h2.resize(N); h3.resize(N); h4.resize(N); tau1 = h1.data(); tau2 = h2.data(); vR = h3.data(); vR2 = h4.data(); }
+    if (patchInterpolation(obs->TS_left.data(), obs->W, obs->H, x1, wx, wy, tau1) &&
+        patchInterpolation(obs->TS_right.data(), obs->W, obs->H, x2, wx, wy, tau2)) {
       if (lsnorm == ESVO_LSNORM_L2) {
         for (int i = 0; i < N; ++i) fvec[i] = tau1[i] - tau2[i];
       } else if (lsnorm == ESVO_LSNORM_ZNCC) {
@@ -375,7 +402,6 @@ struct DepthProblem {
         s1 = std::sqrt(s1 / N) + 1e-6; s2 = std::sqrt(s2 / N) + 1e-6;
         for (int i = 0; i < N; ++i) fvec[i] = ((tau1[i] - m1) / s1 - (tau2[i] - m2) / s2) / std::sqrt((double)N);
       } else {
-        std::vector<double> vR(N), vR2(N);
         double s1 = td_scale2, s2 = -1.0;
         bool first = true;
         while (std::fabs(s2 - s1) / s1 > 0.05 || first) {           // :96
@@ -437,16 +463,39 @@ struct DepthSolver {
     return true;
   }
   // solve + solve_multiple_problems (:28-136), thread-major output order.
-  void solve(const std::vector<Seed>& vEMP, const TsObs& obs, std::vector<DepthPoint>& vdp) {
+  void solve(const std::vector<Seed>& vEMP, const TsObs& obs, std::vector<DepthPoint>& vdp, int exec_threads = 1) {
     vdp.clear(); n_evals = 0;
     const int NT = prm.num_thread_mapping;
     DepthProblem dp; dp.cs = cs; dp.obs = &obs; dp.configure(prm);
+    std::vector<double> dres; std::vector<char> dflag;
+    if (exec_threads > 1) {  // timing legs: same results, solved by exec_threads threads
+      dres.assign(3 * vEMP.size(), 0); dflag.assign(vEMP.size(), 0);
+      std::vector<uint64_t> ev(exec_threads, 0);
+      std::vector<std::thread> th;
+      for (int w = 0; w < exec_threads; ++w)
+        th.emplace_back([&, w]() {
+          DepthSolver me = *this;
+          DepthProblem q; q.cs = cs; q.obs = &obs; q.configure(prm);
+          for (size_t i = w; i < vEMP.size(); i += exec_threads) {
+            q.setProblem(vEMP[i].x_left, vEMP[i].trans);
+            dflag[i] = me.solve_single(vEMP[i].invDepth, q, &dres[3 * i]);
+          }
+          ev[w] = q.n_evals;
+        });
+      for (auto& t : th) t.join();
+      for (auto e : ev) n_evals += e;
+    }
     for (int tid = 0; tid < NT; ++tid)
       for (size_t i = tid; i < vEMP.size(); i += NT) {
         const Seed& s = vEMP[i];
-        dp.setProblem(s.x_left, s.trans);
         double result[3];
-        if (!solve_single(s.invDepth, dp, result)) continue;
+        if (exec_threads > 1) {
+          if (!dflag[i]) continue;
+          result[0] = dres[3 * i]; result[1] = dres[3 * i + 1]; result[2] = dres[3 * i + 2];
+        } else {
+          dp.setProblem(s.x_left, s.trans);
+          if (!solve_single(s.invDepth, dp, result)) continue;
+        }
         DepthPoint d((int64_t)std::floor(s.x_left[1]), (int64_t)std::floor(s.x_left[0]));
         d.x[0] = s.x_left[0]; d.x[1] = s.x_left[1];
         cs->left.cam2World(s.x_left, result[0], d.p_cam);
@@ -459,7 +508,7 @@ struct DepthSolver {
         d.T_world_cam = s.trans;
         vdp.push_back(d);
       }
-    n_evals = dp.n_evals;
+    if (exec_threads <= 1) n_evals = dp.n_evals;
   }
   // pointCulling (:217-244)
   static void cull(std::vector<DepthPoint>& vdp, double std_thr, double cost_thr, double rmin, double rmax) {

@@ -30,6 +30,7 @@ struct esvo_oracle_ctx {
   RegProblem reg;
   TsObs trk_obs;
   uint64_t counters[8] = {0};
+  int exec_threads = 1;   // timing legs only; results do not depend on it
   std::string err;
 };
 
@@ -185,6 +186,7 @@ OAPI int esvo_oracle_map_download(esvo_oracle_ctx* c, esvo_depth_point* out, siz
   *n = cnt;
   return ESVO_OK;
 }
+OAPI int esvo_oracle_set_exec_threads(esvo_oracle_ctx* c, int n) { c->exec_threads = n < 1 ? 1 : n; return ESVO_OK; }
 OAPI int esvo_oracle_mapping_reset(esvo_oracle_ctx* c) { c->window.clear(); return ESVO_OK; }
 
 // MappingAtTime (esvo_Mapping.cpp:261-399) without the optional denoising mask.
@@ -197,9 +199,9 @@ OAPI int esvo_oracle_mapping_at_time(esvo_oracle_ctx* c, const uint16_t* ex, con
   c->T_world_frame = c->obs.tr;
   bm_configure(c);
   std::vector<Seed> vEMP;
-  c->bm.match_all(ex, ey, et, n, pt, poses, np, p.num_thread_mapping, vEMP);
+  c->bm.match_all(ex, ey, et, n, pt, poses, np, p.num_thread_mapping, vEMP, c->exec_threads);
   std::vector<DepthPoint> vdp;
-  c->solver.solve(vEMP, c->obs, vdp);
+  c->solver.solve(vEMP, c->obs, vdp, c->exec_threads);
   size_t n_solved = vdp.size();
   double cost_thr = p.residual_vis_threshold * p.residual_vis_threshold * (p.patch_size_x * p.patch_size_y);
   DepthSolver::cull(vdp, p.stdvar_vis_threshold, cost_thr, p.invdepth_min_range, p.invdepth_max_range);
