@@ -115,7 +115,9 @@ def run_ours(args, rank, world, local_rank):
     g = capi.Backend(prod, l, r, prm, device=local_rank)
     base = make_workload(seed=10 + rank)
     K, Wm = args.steps, args.warmup
-    frames = [shifted(base, k) for k in range(2 * (K + Wm) + 2)]
+    NP = prm.max_num_fusion_frames
+    allf = [shifted(base, k) for k in range(NP + 2 * (K + Wm) + 2)]
+    frames_prime, frames = allf[:NP], allf[NP:]
     stream = torch.cuda.ExternalStream(g.stream(), device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -123,12 +125,13 @@ def run_ours(args, rank, world, local_rank):
         return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
     # ---------------- leg 1: inputs resident in HBM ----------------
-    dframes = []
-    for f in frames[: K + Wm]:
+    def to_dev(f):
         d = {side: {k: dev(v) for k, v in f[side].items()} for side in ("left", "right")}
         d["seeds"] = {k: dev(v) for k, v in f["seeds"].items()}
         d["pose_t"] = dev(f["pose_t"]); d["poses"] = dev(f["poses"])
-        dframes.append(d)
+        return d
+    dframes_prime = [to_dev(f) for f in frames_prime]
+    dframes = [to_dev(f) for f in frames[: K + Wm]]
     torch.cuda.synchronize()
     u16, i64, u8, f64 = C.POINTER(C.c_uint16), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_double)
 
@@ -156,6 +159,9 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
+        # prime the 20-frame fusion window (stream state, like a tracker that has been running), then W warm-up steps
+        for k in range(prm.max_num_fusion_frames):
+            step_resident(frames_prime[k], dframes_prime[k])
         for k in range(Wm):
             step_resident(frames[k], dframes[k])
         g.sync()
@@ -271,7 +277,8 @@ def run_ours(args, rank, world, local_rank):
                                "20-frame window fusion + clean + regularise",
                    "seeds_per_frame": N_SEEDS, "events_per_frame_per_camera": int(base["left"]["x"].size),
                    "parallelism": f"{world} independent streams, one per GPU, no data-path collective",
-                   "l2": "256 MiB write between timed steps (excluded from the per-step CUDA-event timing)"},
+                   "l2": "256 MiB write between timed steps (excluded from the per-step CUDA-event timing)",
+                   "priming": "fusion window filled with max_num_fusion_frames frames before the W warm-up steps"},
         "e2e": {"value": e2e_value, "unit": "evals/s", "ms_per_step": e2e_ms / K, "h2d_bytes_per_step": h2d // K,
                 "d2h_bytes_per_step": d2h // K},
         "gpu_launches": launches,

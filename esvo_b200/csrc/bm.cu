@@ -179,42 +179,49 @@ __device__ int block_excl_scan(int v, int* s_warp, int& total) {
   return res;
 }
 
+// virtual position v in the thread-major order -> event index i
+__device__ __forceinline__ int tm_index(int v, int n, int NT) {
+  int c = 0, start = 0;
+  for (; c < NT; ++c) {
+    const int members = (n > c) ? (n - c + NT - 1) / NT : 0;
+    if (v < start + members) break;
+    start += members;
+  }
+  return c + (v - start) * NT;
+}
+
 __global__ void __launch_bounds__(1024) seeds_order_kernel(DevConsts dc, BmDense d, const uint16_t* __restrict__ ex,
                                                            const uint16_t* __restrict__ ey, const int64_t* __restrict__ et,
                                                            const double* __restrict__ poses, int n, esvo_seed* out,
                                                            unsigned long long* counters) {
   __shared__ int s_warp[33];
-  int running = 0;
   const int NT = dc.NT;
-  for (int c = 0; c < NT; ++c) {
-    const int members = (n > c) ? (n - c + NT - 1) / NT : 0;
-    for (int k0 = 0; k0 < members; k0 += blockDim.x) {
-      const int k = k0 + threadIdx.x;
-      const int i = c + k * NT;
-      const int f = (k < members) ? d.flag[i] : 0;
-      int total;
-      const int pos = running + block_excl_scan(f, s_warp, total);
-      if (f) {
-        esvo_seed s;
-        s.x_left_raw[0] = (double)ex[i]; s.x_left_raw[1] = (double)ey[i];
-        const double xr0 = d.xrect[2 * i], xr1 = d.xrect[2 * i + 1];
-        s.x_left[0] = xr0; s.x_left[1] = xr1;
-        const int x1x = (int)floor(xr0), x1y = (int)floor(xr1), disp = d.disp[i];
-        s.x_right[0] = (double)(dc.updown ? x1x : x1x - disp);
-        s.x_right[1] = (double)(dc.updown ? x1y - disp : x1y);
-        s.t_ns = et[i];
-        const double* T = poses + 16 * (size_t)d.pose_idx[i];
+  const int ipt = (n + blockDim.x - 1) / blockDim.x;
+  const int v0 = threadIdx.x * ipt, v1 = min(n, v0 + ipt);
+  int cnt = 0;
+  for (int v = v0; v < v1; ++v) cnt += d.flag[tm_index(v, n, NT)];
+  int total;
+  int pos = block_excl_scan(cnt, s_warp, total);
+  for (int v = v0; v < v1; ++v) {
+    const int i = tm_index(v, n, NT);
+    if (!d.flag[i]) continue;
+    esvo_seed s;
+    s.x_left_raw[0] = (double)ex[i]; s.x_left_raw[1] = (double)ey[i];
+    const double xr0 = d.xrect[2 * i], xr1 = d.xrect[2 * i + 1];
+    s.x_left[0] = xr0; s.x_left[1] = xr1;
+    const int x1x = (int)floor(xr0), x1y = (int)floor(xr1), disp = d.disp[i];
+    s.x_right[0] = (double)(dc.updown ? x1x : x1x - disp);
+    s.x_right[1] = (double)(dc.updown ? x1y - disp : x1y);
+    s.t_ns = et[i];
+    const double* T = poses + 16 * (size_t)d.pose_idx[i];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) s.T_world_virtual[q] = T[q];
-        const double disparity = (double)disp;
-        const double depth = dc.baseline * dc.Pl[0] / disparity;           // EventBM.cpp:152
-        s.inv_depth = 1.0 / depth; s.cost = d.cost[i]; s.disp = disparity;
-        out[pos] = s;
-      }
-      running += total;
-    }
+    for (int q = 0; q < 16; ++q) s.T_world_virtual[q] = T[q];
+    const double disparity = (double)disp;
+    const double depth = dc.baseline * dc.Pl[0] / disparity;           // EventBM.cpp:152
+    s.inv_depth = 1.0 / depth; s.cost = d.cost[i]; s.disp = disparity;
+    out[pos++] = s;
   }
-  if (threadIdx.x == 0) counters[1] = (unsigned long long)running;
+  if (threadIdx.x == 0) counters[1] = (unsigned long long)total;
 }
 
 // --------------------------------------------------------------------------------------------

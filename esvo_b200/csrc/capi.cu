@@ -46,7 +46,7 @@ int map_alloc_inputs(Ctx* c, size_t n_ev, size_t n_poses) {
   if (n_ev > c->ev_cap) {
     size_t cap = std::max<size_t>(n_ev, 1024);
     void* olds[] = {c->d_ex, c->d_ey, c->d_et, c->bm.flag, c->bm.disp, c->bm.pose_idx, c->bm.cost, c->bm.xrect,
-                    c->d_seeds, c->lm_flag, c->lm_res, c->d_pts};
+                    c->d_seeds, c->lm_flag, c->lm_res, c->d_pts, c->lm_dbg};
     for (void* p : olds) if (p) cudaFree(p);
     ESVO_CUDA_TRY(c, dmalloc(&c->d_ex, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_ey, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_et, cap));
     ESVO_CUDA_TRY(c, dmalloc(&c->bm.flag, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->bm.disp, cap));
@@ -54,6 +54,7 @@ int map_alloc_inputs(Ctx* c, size_t n_ev, size_t n_poses) {
     ESVO_CUDA_TRY(c, dmalloc(&c->bm.xrect, 2 * cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_seeds, cap));
     ESVO_CUDA_TRY(c, dmalloc(&c->lm_flag, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->lm_res, 3 * cap));
     ESVO_CUDA_TRY(c, dmalloc(&c->d_pts, cap));
+    ESVO_CUDA_TRY(c, dmalloc(&c->lm_dbg, 4 * cap));
     c->ev_cap = cap;
   }
   if (n_poses > c->pose_cap) {
@@ -125,6 +126,13 @@ ESVO_API const char* esvo_version(void) { return "esvo_b200 0.1 (sm_100a)"; }
 ESVO_API const char* esvo_last_error(esvo_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
 ESVO_API void* esvo_stream(esvo_ctx* c) { return c ? (void*)c->stream : nullptr; }
 ESVO_API uint64_t esvo_launch_count(esvo_ctx* c) { return c ? c->launches : 0; }
+ESVO_API int esvo_debug_lm_timing(esvo_ctx* c, long long* out, size_t n) {
+  if (!c || !c->lm_dbg) return ESVO_ERR_STATE;
+  cudaSetDevice(c->device);
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpy(out, c->lm_dbg, std::min(n, c->ev_cap) * 32, cudaMemcpyDeviceToHost));
+  return ESVO_OK;
+}
 ESVO_API int esvo_sync(esvo_ctx* c) { CHECK_CTX(c); ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return ESVO_OK; }
 
 ESVO_API esvo_ctx* esvo_create(int device, const esvo_calib* left, const esvo_calib* right, const esvo_params* p,
@@ -191,7 +199,7 @@ ESVO_API void esvo_destroy(esvo_ctx* c) {
   track_free(c);
   void* ps[] = {c->d_lut, c->d_mask, c->obs_l, c->obs_r, c->obs_ls, c->obs_rs, c->d_T_left_world, c->d_counters,
                 c->d_ex, c->d_ey, c->d_et, c->d_pose_t, c->d_poses, c->bm.flag, c->bm.disp, c->bm.pose_idx, c->bm.cost,
-                c->bm.xrect, c->d_seeds, c->lm_flag, c->lm_res, c->d_pts};
+                c->bm.xrect, c->d_seeds, c->lm_flag, c->lm_res, c->d_pts, c->lm_dbg};
   for (void* p : ps) if (p) cudaFree(p);
   for (auto& f : c->win) { cudaFree(f.pts); cudaFree(f.cnt); }
   for (auto& f : c->win_pool) { cudaFree(f.pts); cudaFree(f.cnt); }

@@ -8,6 +8,7 @@ namespace esvo {
 int fuse_zero_fusion_counter(Ctx* c);
 int fuse_fetch_scalars(Ctx* c, unsigned long long out[4]);
 int fuse_reserve(Ctx* c, size_t total_points);
+int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius);
 
 template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
 
@@ -73,9 +74,16 @@ static int run_mapping_frame(Ctx* c) {
   pe = c->prof_begin(5);
   if ((rc = fuse_reset_map(c, c->T_world_left))) return rc;               // :268-272 fresh DepthFrame at the obs pose
   if ((rc = fuse_zero_fusion_counter(c))) return rc;
-  { size_t tot = 0; for (auto& w : c->win) tot += w.cap; if ((rc = fuse_reserve(c, tot))) return rc; }
-  for (auto it = c->win.rbegin(); it != c->win.rend(); ++it)              // :372-377 newest first
-    if ((rc = fuse_points(c, it->pts, it->cap, (const uint64_t*)it->cnt, p.fusion_radius, 0))) return rc;
+  {  // size the staging area once for a full window so that steady-state frames never reallocate
+    size_t tot = 0, mx = 0;
+    for (auto& w : c->win) { tot += w.cap; mx = std::max(mx, w.cap); }
+    if (p.fusion_strategy == ESVO_FUSION_CONST_FRAMES) tot = std::max(tot, mx * (size_t)std::max(1, p.max_num_fusion_frames));
+    if ((rc = fuse_reserve(c, tot))) return rc;
+  }
+  {                                                                       // :372-377 newest first
+    std::vector<Ctx::WinFrame> order(c->win.rbegin(), c->win.rend());
+    if ((rc = fuse_window(c, order.data(), (int)order.size(), p.fusion_radius))) return rc;
+  }
   if ((rc = fuse_finish(c))) return rc;
   if (c->win.size() >= (size_t)p.max_num_fusion_frames)                   // :385-386
     if ((rc = map_clean(c, p.stdvar_vis_threshold * p.stdvar_vis_threshold, p.age_vis_threshold, p.invdepth_max_range,

@@ -59,14 +59,26 @@ __device__ __forceinline__ void cam2world_f(const DevConsts& dc, double x, doubl
 }
 
 // ---- stage: propagate_one_point (:18-68) + splat list insertion (:97-121) ----
-__global__ void fuse_stage_kernel(DevConsts dc, const esvo_depth_point* __restrict__ pts, int n_fixed,
-                                  const unsigned long long* __restrict__ n_ptr, const double* __restrict__ T_frame_world,
+// One launch covers up to FS_MAX vectors of the fusion window (newest first = sequence order).
+constexpr int FS_MAX = 32;
+struct FrameSet {
+  const esvo_depth_point* pts[FS_MAX];
+  const unsigned long long* cnt[FS_MAX];   // device counts (null = use cap)
+  int cap[FS_MAX];
+  int off[FS_MAX + 1];                     // thread / staging offsets (prefix sums of cap)
+  int nframes;
+};
+__global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, const double* __restrict__ T_frame_world,
                                   int radius, int stage_off, PropSoA P, int32_t* head, int32_t* next) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = n_ptr ? (int)*n_ptr : n_fixed;
-  if (j >= n) return;
-  const esvo_depth_point& d = pts[j];
-  const int sid = stage_off + j;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= fs.off[fs.nframes]) return;
+  int f = 0;
+  while (f + 1 < fs.nframes && t >= fs.off[f + 1]) ++f;
+  const int j = t - fs.off[f];
+  const int n = fs.cnt[f] ? (int)*fs.cnt[f] : fs.cap[f];
+  const int sid = stage_off + t;
+  if (j >= n) { P.ok[sid] = 0; return; }
+  const esvo_depth_point& d = fs.pts[f][j];
   // T_frame_obs = T_frame_world * T_world_cam
   double T[12];
 #pragma unroll
@@ -124,7 +136,7 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
   if (h < 0) return;
   head[pix] = -1;
   // The list is in reverse insertion order of the atomics, not in sequence order: collect and sort.
-  constexpr int CAP = 48;
+  constexpr int CAP = 192;
   int ids[CAP];
   int cnt = 0, total = 0;
   for (int q = h; q >= 0; q = next[q]) { if (cnt < CAP) ids[cnt++] = q; ++total; }
@@ -189,7 +201,23 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
     }
   };
   if (total <= CAP) {
-    for (int a = 1; a < cnt; ++a) { int v = ids[a], b = a - 1; while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; } ids[b + 1] = v; }
+    if (cnt <= 16) {
+      for (int a = 1; a < cnt; ++a) { int v = ids[a], b = a - 1; while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; } ids[b + 1] = v; }
+    } else {  // heap sort, O(L log L) on the local array
+      auto sift = [&](int start, int end) {
+        int root = start;
+        while (2 * root + 1 <= end) {
+          int child = 2 * root + 1, sw = root;
+          if (ids[sw] < ids[child]) sw = child;
+          if (child + 1 <= end && ids[sw] < ids[child + 1]) sw = child + 1;
+          if (sw == root) return;
+          int tmp = ids[root]; ids[root] = ids[sw]; ids[sw] = tmp;
+          root = sw;
+        }
+      };
+      for (int st = (cnt - 2) / 2; st >= 0; --st) sift(st, cnt - 1);
+      for (int end = cnt - 1; end > 0; --end) { int tmp = ids[end]; ids[end] = ids[0]; ids[0] = tmp; sift(0, end - 1); }
+    }
     for (int a = 0; a < cnt; ++a) apply(ids[a]);
   } else {  // long list: repeated minimum selection, O(L^2) walks, no storage
     int last = -1;
@@ -384,11 +412,35 @@ int fuse_points(Ctx* c, const esvo_depth_point* d_pts, size_t n_cap, const uint6
     if (rc) return rc;
   }
   const int B = 128;
-  fuse_stage_kernel<<<div_up((int)n_cap, B), B, 0, c->stream>>>(c->dc, d_pts, (int)n_cap, (const unsigned long long*)d_n,
-                                                                ms->d_T_frame_world, radius, (int)ms->staged, ms->p,
+  FrameSet fs;
+  fs.nframes = 1; fs.pts[0] = d_pts; fs.cnt[0] = (const unsigned long long*)d_n; fs.cap[0] = (int)n_cap; fs.off[0] = 0; fs.off[1] = (int)n_cap;
+  fuse_stage_kernel<<<div_up((int)n_cap, B), B, 0, c->stream>>>(c->dc, fs, ms->d_T_frame_world, radius, (int)ms->staged, ms->p,
                                                                 ms->head, ms->next);
   c->launches += 1;
   ms->staged += n_cap;
+  ESVO_CUDA_TRY(c, cudaGetLastError());
+  return ESVO_OK;
+}
+
+// Stage a whole window (vectors given newest first) with as few launches as possible.
+int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
+  MapState* ms = c->map;
+  const int B = 128;
+  for (int f0 = 0; f0 < nframes; f0 += FS_MAX) {
+    FrameSet fs;
+    fs.nframes = std::min(FS_MAX, nframes - f0);
+    fs.off[0] = 0;
+    for (int f = 0; f < fs.nframes; ++f) {
+      fs.pts[f] = frames[f0 + f].pts; fs.cnt[f] = frames[f0 + f].cnt; fs.cap[f] = (int)frames[f0 + f].cap;
+      fs.off[f + 1] = fs.off[f] + fs.cap[f];
+    }
+    const int tot = fs.off[fs.nframes];
+    if (tot == 0) continue;
+    if (ms->staged + (size_t)tot > ms->prop_cap) { c->set_error("fusion staging capacity exceeded"); return ESVO_ERR_CAPACITY; }
+    fuse_stage_kernel<<<div_up(tot, B), B, 0, c->stream>>>(c->dc, fs, ms->d_T_frame_world, radius, (int)ms->staged, ms->p, ms->head, ms->next);
+    c->launches += 1;
+    ms->staged += (size_t)tot;
+  }
   ESVO_CUDA_TRY(c, cudaGetLastError());
   return ESVO_OK;
 }

@@ -334,6 +334,9 @@ struct EventBM {
 // ---------------------------------------------------------------------------------------------
 // DepthProblem (core/DepthProblem.cpp) + DepthProblemSolver (core/DepthProblemSolver.cpp)
 // ---------------------------------------------------------------------------------------------
+static thread_local uint64_t g_irls_iters = 0, g_irls_max = 0;  // diagnostics of the calling thread
+static thread_local uint64_t g_irls_hist[8] = {0};  // non-degenerate evals by iteration count: <=4,<=8,<=16,<=32,<=64,<=256,<=1024,more
+static thread_local uint64_t g_irls_nd_iters = 0, g_irls_deg = 0;
 struct DepthProblem {
   const CameraSystem* cs = nullptr;
   const TsObs* obs = nullptr;
@@ -404,7 +407,9 @@ struct DepthProblem {
       } else {
         double s1 = td_scale2, s2 = -1.0;
         bool first = true;
+        uint64_t loc = 0;
         while (std::fabs(s2 - s1) / s1 > 0.05 || first) {           // :96
+          ++g_irls_iters; if (++loc > g_irls_max) g_irls_max = loc;
           if (!first) s1 = s2;
           double sum = 0;
           for (int i = 0; i < N; ++i) {
@@ -414,6 +419,11 @@ struct DepthProblem {
           if (sum == 0) { s2 = td_scale2; break; }
           s2 = sum / N;
           first = false;
+        }
+        {
+          int nz = 0; for (int i = 0; i < N; ++i) nz += (vR[i] != 0);
+          if ((td_nu + 1) * nz < 0.95 * N) g_irls_deg++;
+          else { g_irls_nd_iters += loc; int b = loc <= 4 ? 0 : loc <= 8 ? 1 : loc <= 16 ? 2 : loc <= 32 ? 3 : loc <= 64 ? 4 : loc <= 256 ? 5 : loc <= 1024 ? 6 : 7; g_irls_hist[b]++; }
         }
         for (int i = 0; i < N; ++i) {
           double weight = (td_nu + 1) / (td_nu + vR2[i] / s2);

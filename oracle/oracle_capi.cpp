@@ -360,4 +360,5 @@ OAPI double esvo_oracle_time_ts_build(esvo_oracle_ctx* c, int cam, int64_t T, in
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
 }
+OAPI void esvo_oracle_op_irls_stats(uint64_t* out) { out[0] = g_irls_iters; out[1] = g_irls_max; g_irls_iters = 0; g_irls_max = 0; out[2] = g_irls_nd_iters; out[3] = g_irls_deg; for (int i = 0; i < 8; ++i) { out[4 + i] = g_irls_hist[i]; g_irls_hist[i] = 0; } g_irls_nd_iters = 0; g_irls_deg = 0; }
 OAPI const char* esvo_oracle_version(void) { return "esvo-oracle 0.1 (CPU restatement, f64)"; }

@@ -113,7 +113,8 @@ def test_depth_solver_parity(oracle_lib, product_lib, rig, lsnorm):
     assert (r < 1e-4).mean() > 0.995, f"{(r >= 1e-4).sum()} of {r.size} seeds beyond 1e-4"
     assert np.median(r) < 1e-7   # forward-difference Jacobian noise: h = 1.5e-8*rho amplifies 1e-16 rounding
     ok = r < 1e-7
-    assert rel(pg["variance"][ok], po["variance"][ok]).max() < 1e-3
+    if lsnorm != capi.LSNORM_ZNCC:   # the reference leaves result[1] uninitialised for "zncc" (DepthProblemSolver.cpp:199-211)
+        assert rel(pg["variance"][ok], po["variance"][ok]).max() < 1e-3
     assert rel(pg["residual"][ok], po["residual"][ok]).max() < 1e-4
     assert np.allclose(pg["p_cam"][ok], po["p_cam"][ok], rtol=1e-6, atol=1e-9)
     assert abs(evo - evg) <= 0.01 * evo
