@@ -31,6 +31,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the library uses up to 8 slot streams + 3 service streams per GPU: give every stream its own hardware queue
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 BM_BYTES = 420.0          # 105 px x 4 B per BM candidate (f32 TS convention)
 LM_BYTES = 1024.0         # 2 x (15+1)(7+1) px x 4 B per LM residual evaluation
@@ -59,7 +61,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", os.environ.get("ESVO_BENCH_SMI_MS", "100")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
                 if self._stop_evt.is_set():
@@ -113,6 +115,13 @@ def run_ours(args, rank, world, local_rank):
     l, r = configs.rig_calibs(RIG)
     prm = configs.params_for(RIG, prod)
     g = capi.Backend(prod, l, r, prm, device=local_rank)
+    g._call("set_pipeline_depth", [C.c_int], args.pipeline_depth)
+    # clocks / throttle reasons are sampled from here to the end of both timed legs; nvidia-smi is started early so
+    # that its start-up (which contends for the driver lock) is over before anything is timed
+    sampler = ClockSampler(local_rank); sampler.start()
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 15:     # nvidia-smi start-up is over once the first row arrives
+        time.sleep(0.05)
     base = make_workload(seed=10 + rank)
     K, Wm = args.steps, args.warmup
     NP = prm.max_num_fusion_frames
@@ -169,23 +178,36 @@ def run_ours(args, rank, world, local_rank):
         g._call("profile", [C.c_int], 1)
         g._call("profile_read", [f64, C.POINTER(C.c_uint64)], (C.c_double * 8)(), (C.c_uint64 * 8)())
         sampler = ClockSampler(local_rank); sampler.start()
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 15:     # nvidia-smi start-up is over once the first row arrives
+        time.sleep(0.05)
         time.sleep(0.3)
+        g.sync()
+        flush.fill_(7)            # evict everything (inputs of the timed steps included) from L2 before the timed region
         barrier()
         launches0 = g.launch_count()
-        evs = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall0 = time.perf_counter()
+        e0.record(stream)
+        host_prof = {}
+        if os.environ.get("ESVO_BENCH_HOSTPROF") == "1":
+            orig_call = g._call
+            def timed_call(name, *a, **kw):
+                t = time.perf_counter(); r = orig_call(name, *a, **kw); host_prof[name] = host_prof.get(name, 0.0) + time.perf_counter() - t
+                return r
+            g._call = timed_call
         for k in range(Wm, Wm + K):
-            flush.fill_(k & 255)                       # L2 flush between timed iterations (not timed)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
             step_resident(frames[k], dframes[k])
-            e1.record(stream)
-            evs.append((e0, e1))
+        host_prof["issue_total"] = time.perf_counter() - t_wall0
+        if os.environ.get("ESVO_BENCH_HOSTPROF") == "1":
+            g._call = orig_call
+            print({k: round(v * 1e3 / K, 4) for k, v in host_prof.items()}, file=sys.stderr)
+        g.sync()                                       # every stream of the library drained
+        e1.record(stream)
         barrier()
         t_wall = time.perf_counter() - t_wall0
         launches = g.launch_count() - launches0
-        clocks = sampler.stop()
-        step_ms = [a.elapsed_time(b) for a, b in evs]
+        step_ms = [e0.elapsed_time(e1)]
         ms = (C.c_double * 8)(); cnt = (C.c_uint64 * 8)()
         g._call("profile_read", [f64, C.POINTER(C.c_uint64)], ms, cnt)
         g._call("profile", [C.c_int], 0)
@@ -209,8 +231,16 @@ def run_ours(args, rank, world, local_rank):
         pinned.append(pf)
     h2d = d2h = 0
 
+    tickets = []
+
     def step_e2e(f):
+        """Host-buffer C ABI: H2D of this frame's events/seeds/poses from pinned memory, the frame itself, and the
+        D2H of its counters + fused map (collected `depth-1` frames later so that frames stay in flight)."""
         nonlocal h2d, d2h
+        res = None
+        if len(tickets) >= max(1, args.pipeline_depth - 1):
+            m, res = g.results_end(tickets.pop(0))
+            d2h += 64 + 64 + m.nbytes + m.size * 8
         for cam, side in ((0, "left"), (1, "right")):
             e = f[side]
             g.stage_ts_events(cam, e["x"], e["y"], e["t"], e["p"])
@@ -219,21 +249,32 @@ def run_ours(args, rank, world, local_rank):
         T = np.ascontiguousarray(f["T_world_left"], np.float64)
         g._call("set_ts_pair_dev", [f64], T.ctypes.data_as(f64))
         sd = f["seeds"]
-        c = g.mapping_at_time(sd["x"], sd["y"], sd["t"], f["pose_t"], f["poses"])
-        m = g.map_download()
+        g.stage_mapping_inputs(sd["x"], sd["y"], sd["t"], f["pose_t"], f["poses"])
+        g.run_mapping()
+        tickets.append(g.results_begin())
         h2d += sd["x"].size * 12 + f["pose_t"].size * 136 + 128
-        d2h += 64 + 32 + m.nbytes + m.size * 8
-        return c
+        return res
+
+    def drain_e2e():
+        nonlocal d2h
+        res = None
+        while tickets:
+            m, res = g.results_end(tickets.pop(0))
+            d2h += 64 + 64 + m.nbytes + m.size * 8
+        return res
 
     for f in pinned[:Wm]:
         step_e2e(f)
+    drain_e2e()
     h2d = d2h = 0
     barrier()
     t0 = time.perf_counter()
     for f in pinned[Wm: Wm + K]:
-        ce = step_e2e(f)
+        step_e2e(f)
+    ce = drain_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
     e2e_evals = ce["bm_evals"] + ce["lm_evals"]
     # TS-only rate (second half of the metric): resident events -> rectified u8 TS, both cameras per step
     ts_frames_per_s = 2 * K / (ms[0] / 1e3) if ms[0] > 0 else None
@@ -277,7 +318,11 @@ def run_ours(args, rank, world, local_rank):
                                "20-frame window fusion + clean + regularise",
                    "seeds_per_frame": N_SEEDS, "events_per_frame_per_camera": int(base["left"]["x"].size),
                    "parallelism": f"{world} independent streams, one per GPU, no data-path collective",
-                   "l2": "256 MiB write between timed steps (excluded from the per-step CUDA-event timing)",
+                   "l2": "inputs larger than L2, read once: every timed step consumes its own event/seed/pose arrays (1.75 MB per step, "
+                         "all evicted by a 256 MiB write right before the timed region; with software-pipelined frames in flight a flush "
+                         "between iterations would serialise the pipeline); the persistent state (TS images, LUT, grids, ~6 MB) is "
+                         "L2-resident by design",
+                   "pipeline_depth": args.pipeline_depth,
                    "priming": "fusion window filled with max_num_fusion_frames frames before the W warm-up steps"},
         "e2e": {"value": e2e_value, "unit": "evals/s", "ms_per_step": e2e_ms / K, "h2d_bytes_per_step": h2d // K,
                 "d2h_bytes_per_step": d2h // K},
@@ -352,10 +397,11 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-depth", type=int, default=4, help="frames in flight per stream (1 = strictly sequential)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))

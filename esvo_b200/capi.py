@@ -356,6 +356,25 @@ class Backend:
         keys = ["n_events", "n_seeds", "n_solved", "n_culled", "n_fusions", "bm_evals", "lm_evals", "map_size"]
         return dict(zip(keys, [int(v) for v in ctr]))
 
+    def set_pipeline_depth(self, depth):
+        self._call("set_pipeline_depth", [C.c_int], int(depth))
+
+    def results_begin(self):
+        t = C.c_int64(-1)
+        self._call("results_begin", [C.POINTER(C.c_int64)], C.byref(t))
+        return t.value
+
+    def results_end(self, ticket):
+        if not hasattr(self, "_res_buf"):
+            self._res_buf = np.zeros(self.W * self.H, DEPTH_POINT_DTYPE)
+        out = self._res_buf
+        n = C.c_size_t(out.size)
+        ctr = (C.c_uint64 * 8)()
+        self._call("results_end", [C.c_int64, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)],
+                   int(ticket), out.ctypes.data_as(C.c_void_p), C.byref(n), ctr)
+        keys = ["n_events", "n_seeds", "n_solved", "n_culled", "n_fusions", "bm_evals", "lm_evals", "map_size"]
+        return out[: n.value], dict(zip(keys, [int(v) for v in ctr]))
+
     def sync(self):
         self._call("sync", [])
 

@@ -36,6 +36,7 @@ __global__ void gauss5_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __res
 
 int smooth_obs(Ctx* c) {
   dim3 b(32, 8), g(div_up(c->dc.W, 32), div_up(c->dc.H, 8));
+  c->obs_ls = c->slots[c->cur].own_ls; c->obs_rs = c->slots[c->cur].own_rs;
   gauss5_u8_kernel<<<g, b, 0, c->stream>>>(c->obs_l, c->obs_ls, c->dc.W, c->dc.H, c->dc.pitch);
   gauss5_u8_kernel<<<g, b, 0, c->stream>>>(c->obs_r, c->obs_rs, c->dc.W, c->dc.H, c->dc.pitch);
   c->launches += 2;
@@ -64,6 +65,53 @@ int map_alloc_inputs(Ctx* c, size_t n_ev, size_t n_poses) {
     ESVO_CUDA_TRY(c, dmalloc(&c->d_pose_t, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_poses, 16 * cap));
     c->pose_cap = cap;
   }
+  return ESVO_OK;
+}
+
+#define SLOT_FIELDS(X) X(obs_l) X(obs_r) X(obs_ls) X(obs_rs) X(d_T_left_world) X(ev_cap) X(pose_cap) X(n_ev) X(n_poses) \
+  X(d_ex) X(d_ey) X(d_et) X(d_pose_t) X(d_poses) X(bm) X(d_seeds) X(lm_flag) X(lm_res) X(lm_dbg) X(d_pts) X(d_counters) \
+  X(h_counters) X(h_pin)
+void slot_save(Ctx* c) {
+  SlotBufs& s = c->slots[c->cur];
+#define X(f) s.f = c->f;
+  SLOT_FIELDS(X)
+#undef X
+  std::memcpy(s.T_world_left, c->T_world_left, sizeof(s.T_world_left));
+}
+void slot_load(Ctx* c, int i) {
+  SlotBufs& s = c->slots[i];
+#define X(f) c->f = s.f;
+  SLOT_FIELDS(X)
+#undef X
+  std::memcpy(c->T_world_left, s.T_world_left, sizeof(s.T_world_left));
+  c->cur = i;
+  c->stream = s.stream;
+}
+int slot_alloc(Ctx* c, int i) {
+  SlotBufs& s = c->slots[i];
+  if (s.allocated) return ESVO_OK;
+  const size_t nimg = (size_t)c->dc.pitch * c->dc.H;
+  if (!s.stream) ESVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  ESVO_CUDA_TRY(c, dmalloc(&s.obs_l, nimg)); ESVO_CUDA_TRY(c, dmalloc(&s.obs_r, nimg));
+  ESVO_CUDA_TRY(c, dmalloc(&s.own_ls, nimg)); ESVO_CUDA_TRY(c, dmalloc(&s.own_rs, nimg));
+  s.obs_ls = s.own_ls; s.obs_rs = s.own_rs;
+  ESVO_CUDA_TRY(c, dmalloc(&s.d_T_left_world, 16)); ESVO_CUDA_TRY(c, dmalloc(&s.d_counters, kCounters));
+  ESVO_CUDA_TRY(c, cudaMallocHost((void**)&s.h_counters, kCounters * 8));
+  ESVO_CUDA_TRY(c, cudaMallocHost((void**)&s.h_pin, 64 * 8));
+  ESVO_CUDA_TRY(c, cudaMemset(s.d_counters, 0, kCounters * 8));
+  ESVO_CUDA_TRY(c, cudaMemset(s.obs_l, 0, nimg)); ESVO_CUDA_TRY(c, cudaMemset(s.obs_r, 0, nimg));
+  ESVO_CUDA_TRY(c, cudaMemset(s.own_ls, 0, nimg)); ESVO_CUDA_TRY(c, cudaMemset(s.own_rs, 0, nimg));
+  ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&s.ev_obs, cudaEventDisableTiming));
+  ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&s.ev_free, cudaEventDisableTiming));
+  ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&s.ev_pts, cudaEventDisableTiming));
+  s.allocated = true;
+  return ESVO_OK;
+}
+int drain(Ctx* c) {
+  if (c->s_ts) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_ts));
+  for (int i = 0; i < kMaxSlots; ++i) if (c->slots[i].stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->slots[i].stream));
+  if (c->s_fuse) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_fuse));
+  if (c->s_copy) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
   return ESVO_OK;
 }
 
@@ -133,7 +181,26 @@ ESVO_API int esvo_debug_lm_timing(esvo_ctx* c, long long* out, size_t n) {
   ESVO_CUDA_TRY(c, cudaMemcpy(out, c->lm_dbg, std::min(n, c->ev_cap) * 32, cudaMemcpyDeviceToHost));
   return ESVO_OK;
 }
-ESVO_API int esvo_sync(esvo_ctx* c) { CHECK_CTX(c); ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return ESVO_OK; }
+ESVO_API int esvo_sync(esvo_ctx* c) { CHECK_CTX(c); return drain(c); }
+ESVO_API int esvo_set_pipeline_depth(esvo_ctx* c, int depth) {
+  CHECK_CTX(c);
+  if (depth < 1 || depth > kMaxSlots) return ESVO_ERR_INVALID_ARG;
+  int rc = drain(c);
+  if (rc) return rc;
+  slot_save(c);
+  if (depth > 1) {
+    if (c->s_ts == c->s_main) ESVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_ts, cudaStreamNonBlocking));
+    if (c->s_fuse == c->s_main) ESVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_fuse, cudaStreamNonBlocking));
+    for (int i = 1; i < depth; ++i) if ((rc = slot_alloc(c, i))) return rc;
+  } else {
+    if (c->s_ts != c->s_main) { cudaStreamDestroy(c->s_ts); c->s_ts = c->s_main; }
+    if (c->s_fuse != c->s_main) { cudaStreamDestroy(c->s_fuse); c->s_fuse = c->s_main; }
+  }
+  c->depth = depth;
+  c->frame_no = 0;
+  slot_load(c, 0);
+  return ESVO_OK;
+}
 
 ESVO_API esvo_ctx* esvo_create(int device, const esvo_calib* left, const esvo_calib* right, const esvo_params* p,
                                int* status_out) {
@@ -172,15 +239,14 @@ ESVO_API esvo_ctx* esvo_create(int device, const esvo_calib* left, const esvo_ca
   d.NT = std::max(1, p->num_thread_mapping);
   if (d.dmax >= d.dmin && (d.dmax - d.dmin) / d.step + 1 > 192 && d.step > 1) { delete c; return fail(ESVO_ERR_UNSUPPORTED); }
   auto bail = [&](int code) -> esvo_ctx* { esvo_destroy(c); return fail(code); };
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ESVO_ERR_CUDA);
-  const size_t npix = (size_t)d.W * d.H, nimg = (size_t)d.pitch * d.H;
-  if (dmalloc(&c->d_lut, 2 * npix) || dmalloc(&c->d_mask, npix) || dmalloc(&c->obs_l, nimg) || dmalloc(&c->obs_r, nimg) ||
-      dmalloc(&c->obs_ls, nimg) || dmalloc(&c->obs_rs, nimg) || dmalloc(&c->d_T_left_world, 16) ||
-      dmalloc(&c->d_counters, kCounters) || cudaMallocHost((void**)&c->h_counters, kCounters * 8) ||
-      cudaMallocHost((void**)&c->h_pin, 64 * 8))
-    return bail(ESVO_ERR_CUDA);
-  cudaMemset(c->d_counters, 0, kCounters * 8);
-  cudaMemset(c->obs_l, 0, nimg); cudaMemset(c->obs_r, 0, nimg); cudaMemset(c->obs_ls, 0, nimg); cudaMemset(c->obs_rs, 0, nimg);
+  if (cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) != cudaSuccess) return bail(ESVO_ERR_CUDA);
+  c->stream = c->s_ts = c->s_fuse = c->s_main;
+  c->slots[0].stream = c->s_main;
+  const size_t npix = (size_t)d.W * d.H;
+  if (slot_alloc(c, 0)) return bail(ESVO_ERR_CUDA);
+  slot_load(c, 0);
+  if (cudaEventCreateWithFlags(&c->ev_fuse_done, cudaEventDisableTiming) != cudaSuccess) return bail(ESVO_ERR_CUDA);
+  if (dmalloc(&c->d_lut, 2 * npix) || dmalloc(&c->d_mask, npix)) return bail(ESVO_ERR_CUDA);
   for (int cam = 0; cam < 2; ++cam) if (ts_alloc(c, cam)) return bail(ESVO_ERR_CUDA);
   if (upload_tables(c)) return bail(ESVO_ERR_CUDA);
   if (map_alloc_inputs(c, 16384, 512)) return bail(ESVO_ERR_CUDA);
@@ -193,21 +259,42 @@ ESVO_API esvo_ctx* esvo_create(int device, const esvo_calib* left, const esvo_ca
 ESVO_API void esvo_destroy(esvo_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
+  drain(c);
+  if (c->slots[0].allocated) slot_save(c);
+  c->stream = c->s_main;
   for (int cam = 0; cam < 2; ++cam) ts_free(c, cam);
   fuse_free(c);
   track_free(c);
-  void* ps[] = {c->d_lut, c->d_mask, c->obs_l, c->obs_r, c->obs_ls, c->obs_rs, c->d_T_left_world, c->d_counters,
-                c->d_ex, c->d_ey, c->d_et, c->d_pose_t, c->d_poses, c->bm.flag, c->bm.disp, c->bm.pose_idx, c->bm.cost,
-                c->bm.xrect, c->d_seeds, c->lm_flag, c->lm_res, c->d_pts, c->lm_dbg};
-  for (void* p : ps) if (p) cudaFree(p);
+  if (c->d_lut) cudaFree(c->d_lut);
+  if (c->d_mask) cudaFree(c->d_mask);
+  for (int i = 0; i < kMaxSlots; ++i) {
+    SlotBufs& s = c->slots[i];
+    void* ps[] = {s.obs_l, s.obs_r, s.own_ls, s.own_rs, s.d_T_left_world, s.d_counters, s.d_ex, s.d_ey, s.d_et, s.d_pose_t,
+                  s.d_poses, s.bm.flag, s.bm.disp, s.bm.pose_idx, s.bm.cost, s.bm.xrect, s.d_seeds, s.lm_flag, s.lm_res,
+                  s.d_pts, s.lm_dbg};
+    for (void* p : ps) if (p) cudaFree(p);
+    if (s.h_counters) cudaFreeHost(s.h_counters);
+    if (s.h_pin) cudaFreeHost(s.h_pin);
+    if (s.ev_obs) cudaEventDestroy(s.ev_obs);
+    if (s.ev_free) cudaEventDestroy(s.ev_free);
+    if (s.ev_pts) cudaEventDestroy(s.ev_pts);
+    if (s.ev_dl) cudaEventDestroy(s.ev_dl);
+    if (s.d_dl) cudaFree(s.d_dl);
+    if (s.d_dl_keys) cudaFree(s.d_dl_keys);
+    if (s.d_dlscal) cudaFree(s.d_dlscal);
+    if (s.h_dlscal) cudaFreeHost(s.h_dlscal);
+    if (s.h_dl) cudaFreeHost(s.h_dl);
+    if (s.stream && s.stream != c->s_main) cudaStreamDestroy(s.stream);
+  }
   for (auto& f : c->win) { cudaFree(f.pts); cudaFree(f.cnt); }
   for (auto& f : c->win_pool) { cudaFree(f.pts); cudaFree(f.cnt); }
-  if (c->h_counters) cudaFreeHost(c->h_counters);
-  if (c->h_pin) cudaFreeHost(c->h_pin);
   for (auto e : c->prof_pool) cudaEventDestroy(e);
+  if (c->ev_fuse_done) cudaEventDestroy(c->ev_fuse_done);
   if (c->h_stage) cudaFreeHost(c->h_stage);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->s_ts && c->s_ts != c->s_main) cudaStreamDestroy(c->s_ts);
+  if (c->s_fuse && c->s_fuse != c->s_main) cudaStreamDestroy(c->s_fuse);
+  if (c->s_copy) cudaStreamDestroy(c->s_copy);
+  if (c->s_main) cudaStreamDestroy(c->s_main);
   delete c;
 }
 
@@ -244,12 +331,14 @@ ESVO_API int esvo_stage_ts_events(esvo_ctx* c, int cam, const uint16_t* x, const
                                   const uint8_t* pol, size_t n) {
   CHECK_CTX(c);
   if (cam < 0 || cam > 1 || (n && (!x || !y || !t))) return ESVO_ERR_INVALID_ARG;
+  StreamScope sc(c, c->s_ts);
   return ts_push(c, cam, x, y, t, pol, n, false);
 }
 ESVO_API int esvo_ts_push_events_dev(esvo_ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t,
                                      const uint8_t* pol, size_t n) {
   CHECK_CTX(c);
   if (cam < 0 || cam > 1 || (n && (!x || !y || !t))) return ESVO_ERR_INVALID_ARG;
+  StreamScope sc(c, c->s_ts);
   return ts_push(c, cam, x, y, t, pol, n, true);
 }
 ESVO_API int esvo_ts_push_events(esvo_ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t,
@@ -257,12 +346,13 @@ ESVO_API int esvo_ts_push_events(esvo_ctx* c, int cam, const uint16_t* x, const 
   int rc = esvo_stage_ts_events(c, cam, x, y, t, pol, n);
   if (rc) return rc;
   // the caller's buffers may be reused as soon as we return
-  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_ts));
   return ESVO_OK;
 }
 ESVO_API int esvo_run_ts_build(esvo_ctx* c, int cam, int64_t T) {
   CHECK_CTX(c);
   if (cam < 0 || cam > 1) return ESVO_ERR_INVALID_ARG;
+  StreamScope sc(c, c->s_ts);
   return ts_run_build(c, cam, T);
 }
 ESVO_API int esvo_ts_build(esvo_ctx* c, int cam, int64_t T, int64_t* idx_out, uint8_t* ts_out) {
@@ -270,17 +360,21 @@ ESVO_API int esvo_ts_build(esvo_ctx* c, int cam, int64_t T, int64_t* idx_out, ui
   if (rc) return rc;
   TsState& s = c->ts[cam];
   const DevConsts& d = c->dc;
+  StreamScope sc(c, c->s_ts);
   if (idx_out) ESVO_CUDA_TRY(c, cudaMemcpyAsync(idx_out, s.out_idx, (size_t)d.W * d.H * 8, cudaMemcpyDeviceToHost, c->stream));
   if (ts_out) ESVO_CUDA_TRY(c, cudaMemcpy2DAsync(ts_out, d.W, s.img_out, d.pitch, d.W, d.H, cudaMemcpyDeviceToHost, c->stream));
-  int32_t sc[4] = {0, 0, 0, 0};
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(sc, s.scalars, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
+  int32_t flags[4] = {0, 0, 0, 0};
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(flags, s.scalars, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
   ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  if (sc[1]) { c->set_error("events were not pushed in time order (unsupported on the device path)"); return ESVO_ERR_UNSUPPORTED; }
+  if (flags[1]) { c->set_error("events were not pushed in time order (unsupported on the device path)"); return ESVO_ERR_UNSUPPORTED; }
   return ESVO_OK;
 }
 ESVO_API int esvo_ts_reset(esvo_ctx* c, int cam) {
   CHECK_CTX(c);
   if (cam < 0 || cam > 1) return ESVO_ERR_INVALID_ARG;
+  int rc = drain(c);
+  if (rc) return rc;
+  StreamScope sc(c, c->s_ts);
   return ts_reset_state(c, cam);
 }
 
@@ -288,25 +382,30 @@ ESVO_API int esvo_ts_reset(esvo_ctx* c, int cam) {
 ESVO_API int esvo_set_ts_pair(esvo_ctx* c, const uint8_t* l, const uint8_t* r, const double T[16]) {
   CHECK_CTX(c);
   if (!T) return ESVO_ERR_INVALID_ARG;
+  { int rc0 = drain(c); if (rc0) return rc0; }
   const DevConsts& d = c->dc;
   const size_t nimg = (size_t)d.pitch * d.H;
   if (l) ESVO_CUDA_TRY(c, cudaMemcpy2DAsync(c->obs_l, d.pitch, l, d.W, d.W, d.H, cudaMemcpyHostToDevice, c->stream));
   else {
     if (!c->ts[0].built) { c->set_error("ts_left == NULL but no time surface was built for camera 0"); return ESVO_ERR_STATE; }
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_l, c->ts[0].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->obs_l != c->ts[0].last_img) ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_l, c->ts[0].last_img, nimg, cudaMemcpyDeviceToDevice, c->stream));
   }
   if (r) ESVO_CUDA_TRY(c, cudaMemcpy2DAsync(c->obs_r, d.pitch, r, d.W, d.W, d.H, cudaMemcpyHostToDevice, c->stream));
   else {
     if (!c->ts[1].built) { c->set_error("ts_right == NULL but no time surface was built for camera 1"); return ESVO_ERR_STATE; }
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_r, c->ts[1].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->obs_r != c->ts[1].last_img) ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_r, c->ts[1].last_img, nimg, cudaMemcpyDeviceToDevice, c->stream));
   }
   std::memcpy(c->T_world_left, T, sizeof(c->T_world_left));
   double Ti[16];
   rigid_inverse(T, Ti);
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_T_left_world, Ti, sizeof(Ti), cudaMemcpyHostToDevice, c->stream));
   // Until createMatchProblem smooths it, the observation the solver reads is the raw pair.
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_ls, c->obs_l, nimg, cudaMemcpyDeviceToDevice, c->stream));
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_rs, c->obs_r, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  if (!c->prm.smooth_time_surface) { c->obs_ls = c->obs_l; c->obs_rs = c->obs_r; }
+  else {
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_ls, c->obs_l, nimg, cudaMemcpyDeviceToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_rs, c->obs_r, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  ESVO_CUDA_TRY(c, cudaEventRecord(c->slots[c->cur].ev_obs, c->stream));
   ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // Ti and the caller's images are host stack/heap
   c->obs_set = true;
   return ESVO_OK;
@@ -316,17 +415,27 @@ ESVO_API int esvo_set_ts_pair_dev(esvo_ctx* c, const double T[16]) {
   CHECK_CTX(c);
   if (!T) return ESVO_ERR_INVALID_ARG;
   if (!c->ts[0].built || !c->ts[1].built) { c->set_error("esvo_set_ts_pair_dev needs a built time surface for both cameras"); return ESVO_ERR_STATE; }
-  const size_t nimg = (size_t)c->dc.pitch * c->dc.H;
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_l, c->ts[0].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_r, c->ts[1].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_ls, c->ts[0].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_rs, c->ts[1].img_out, nimg, cudaMemcpyDeviceToDevice, c->stream));
+  // begin a new frame: rotate to the next pipeline slot
+  slot_save(c);
+  slot_load(c, (int)(c->frame_no % (uint64_t)c->depth));
+  SlotBufs& sl = c->slots[c->cur];
+  // Hand the two freshly built images to the slot WITHOUT copying: swap the slot's observation buffers with
+  // the time-surface output buffers.  The buffers the TS state receives in exchange are overwritten by the
+  // next build, so the TS stream must first wait until the slot's previous frame stopped reading them.
+  if (sl.ev_free_valid) ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->s_ts, sl.ev_free, 0));
+  ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_obs, c->s_ts));   // both builds of this frame are complete at this point
+  for (int cam = 0; cam < 2; ++cam) {
+    TsState& t = c->ts[cam];
+    if (t.last_img != t.img_out) { c->set_error("esvo_set_ts_pair_dev: time surface not rebuilt since the last hand-off"); return ESVO_ERR_STATE; }
+    uint8_t*& mine = cam == 0 ? c->obs_l : c->obs_r;
+    std::swap(mine, t.img_out);
+    t.last_img = mine;
+  }
+  if (!c->prm.smooth_time_surface) { c->obs_ls = c->obs_l; c->obs_rs = c->obs_r; }   // otherwise smooth_obs() fills obs_ls/obs_rs
   std::memcpy(c->T_world_left, T, sizeof(c->T_world_left));
-  // the pinned block may still be in flight from the previous frame: double buffer by parity
-  static thread_local int flip = 0;
-  double* Ti = c->h_pin + 16 * (flip++ & 1);
-  rigid_inverse(T, Ti);
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_T_left_world, Ti, 128, cudaMemcpyHostToDevice, c->stream));
+  // pinned block of this slot: its previous upload finished long ago (same stream, S frames back)
+  rigid_inverse(T, c->h_pin);
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_T_left_world, c->h_pin, 128, cudaMemcpyHostToDevice, c->stream));
   c->obs_set = true;
   return ESVO_OK;
 }
@@ -343,6 +452,7 @@ ESVO_API int esvo_bm_match(esvo_ctx* c, const uint16_t* ex, const uint16_t* ey, 
                            const int64_t* pt, const double* poses, size_t np, esvo_seed* out, size_t* n_seeds,
                            uint64_t* n_evals) {
   CHECK_CTX(c);
+  if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }
   if (!c->obs_set) return ESVO_ERR_STATE;
   if (!n_seeds || (n && (!ex || !ey || !et))) return ESVO_ERR_INVALID_ARG;
   int rc = stage_mapping(c, ex, ey, et, n, pt, poses, np);
@@ -361,6 +471,7 @@ ESVO_API int esvo_bm_match(esvo_ctx* c, const uint16_t* ex, const uint16_t* ey, 
 ESVO_API int esvo_depth_solve(esvo_ctx* c, const esvo_seed* seeds, size_t n, esvo_depth_point* out, size_t* n_out,
                               uint64_t* n_evals) {
   CHECK_CTX(c);
+  if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }
   if (!c->obs_set) return ESVO_ERR_STATE;
   if (!n_out || (n && !seeds)) return ESVO_ERR_INVALID_ARG;
   if (n == 0) { *n_out = 0; if (n_evals) *n_evals = 0; return ESVO_OK; }

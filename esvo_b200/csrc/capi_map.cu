@@ -32,6 +32,8 @@ static int fetch_counters2(Ctx* c) {
 static int run_mapping_frame(Ctx* c) {
   const esvo_params& p = c->prm;
   int rc;
+  SlotBufs& sl = c->slots[c->cur];
+  ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, sl.ev_obs, 0));        // observation of this frame is in place
   cudaEvent_t pe = c->prof_begin(1);
   if (p.smooth_time_surface && (rc = smooth_obs(c))) return rc;           // createMatchProblem (EventBM.cpp:68-72)
   ESVO_CUDA_TRY(c, cudaMemsetAsync(c->d_counters, 0, kCounters * 8, c->stream));
@@ -41,6 +43,10 @@ static int run_mapping_frame(Ctx* c) {
   c->prof_end(pe); pe = c->prof_begin(3);
   if ((rc = lm_run(c, c->d_seeds, 0))) return rc;                         // :330
   c->prof_end(pe);
+  ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_free, c->stream));               // the slot's observation buffers are free again
+  sl.ev_free_valid = true;
+  // the window buffer we are about to overwrite may still be read by the previous frame's fusion
+  if (c->fuse_ever && c->s_fuse != c->stream) ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_fuse_done, 0));
   Ctx::WinFrame f;
   if ((rc = win_acquire(c, std::max<size_t>(c->n_ev, 1), f))) return rc;
   const double cost_thr = p.residual_vis_threshold * p.residual_vis_threshold * (double)(p.patch_size_x * p.patch_size_y);
@@ -71,6 +77,9 @@ static int run_mapping_frame(Ctx* c) {
   } else {
     while (c->win.size() > (size_t)p.max_num_fusion_frames) { c->win_pool.push_back(c->win.front()); c->win.erase(c->win.begin()); }
   }
+  ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_pts, c->stream));
+  StreamScope fuse_scope(c, c->s_fuse);                                   // the map is shared state: its own stream
+  ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->s_fuse, sl.ev_pts, 0));
   pe = c->prof_begin(5);
   if ((rc = fuse_reset_map(c, c->T_world_left))) return rc;               // :268-272 fresh DepthFrame at the obs pose
   if ((rc = fuse_zero_fusion_counter(c))) return rc;
@@ -92,10 +101,14 @@ static int run_mapping_frame(Ctx* c) {
   if (p.regularization && (rc = map_regularize(c))) return rc;            // :390-395
   rc = map_count(c);
   c->prof_end(pe);
+  ESVO_CUDA_TRY(c, cudaEventRecord(c->ev_fuse_done, c->s_fuse));
+  c->fuse_ever = true;
+  c->frame_no++;
   return rc;
 }
 
 static int fetch_mapping_counters(Ctx* c, uint64_t out[8]) {
+  if (c->s_fuse != c->stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_fuse));
   int rc = fetch_counters2(c);
   if (rc) return rc;
   unsigned long long sc[4];
@@ -114,6 +127,7 @@ extern "C" {
 ESVO_API int esvo_depth_cull(esvo_ctx* c, esvo_depth_point* pts, size_t* n, double std_thr, double cost_thr,
                              double rmin, double rmax) {
   CHECK_CTX(c);
+  if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }
   if (!n || (*n && !pts)) return ESVO_ERR_INVALID_ARG;
   if (*n == 0) return ESVO_OK;
   int rc = map_alloc_inputs(c, std::max(*n, c->n_ev), c->n_poses);
@@ -135,6 +149,7 @@ ESVO_API int esvo_depth_cull(esvo_ctx* c, esvo_depth_point* pts, size_t* n, doub
 ESVO_API int esvo_fuse(esvo_ctx* c, const esvo_depth_point* pts, size_t n, const double T[16], int radius, int reset_map,
                        int* n_fusions) {
   CHECK_CTX(c);
+  if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }
   if (n && !pts) return ESVO_ERR_INVALID_ARG;
   int rc;
   if (reset_map) { if (!T) return ESVO_ERR_INVALID_ARG; if ((rc = fuse_reset_map(c, T))) return rc; }
@@ -155,16 +170,19 @@ ESVO_API int esvo_fuse(esvo_ctx* c, const esvo_depth_point* pts, size_t n, const
 
 ESVO_API int esvo_map_clean(esvo_ctx* c, double var_thr, double age_thr, double rmax, double rmin) {
   CHECK_CTX(c);
+  if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }
   return map_clean(c, var_thr, age_thr, rmax, rmin);
 }
-ESVO_API int esvo_map_regularize(esvo_ctx* c) { CHECK_CTX(c); return map_regularize(c); }
+ESVO_API int esvo_map_regularize(esvo_ctx* c) { CHECK_CTX(c); if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; } return map_regularize(c); }
 ESVO_API int esvo_map_download(esvo_ctx* c, esvo_depth_point* out, size_t* n) {
   CHECK_CTX(c);
   if (!n) return ESVO_ERR_INVALID_ARG;
+  if (c->depth > 1 || c->s_fuse != c->stream) { int rc0 = drain(c); if (rc0) return rc0; }
   return map_download(c, out, n);
 }
 ESVO_API int esvo_mapping_reset(esvo_ctx* c) {
   CHECK_CTX(c);
+  { int rc0 = drain(c); if (rc0) return rc0; }
   for (auto& f : c->win) c->win_pool.push_back(f);
   c->win.clear();
   return ESVO_OK;
@@ -206,6 +224,65 @@ ESVO_API int esvo_stage_mapping_inputs_dev(esvo_ctx* c, const uint16_t* ex, cons
     ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_pose_t, pt, np * 8, cudaMemcpyDeviceToDevice, c->stream));
     ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_poses, poses, np * 16 * 8, cudaMemcpyDeviceToDevice, c->stream));
   }
+  return ESVO_OK;
+}
+// ---- asynchronous result hand-off for pipelined operation ----
+ESVO_API int esvo_results_begin(esvo_ctx* c, int64_t* ticket_out) {
+  CHECK_CTX(c);
+  if (c->frame_no == 0) return ESVO_ERR_STATE;
+  slot_save(c);
+  SlotBufs& sl = c->slots[c->cur];
+  if (sl.dl_ticket >= 0) { c->set_error("esvo_results_begin: the previous results of this pipeline slot were not collected"); return ESVO_ERR_STATE; }
+  const size_t npix = (size_t)c->dc.W * c->dc.H;
+  if (!sl.d_dl) {
+    ESVO_CUDA_TRY(c, dmalloc(&sl.d_dl, npix)); ESVO_CUDA_TRY(c, dmalloc(&sl.d_dl_keys, npix)); ESVO_CUDA_TRY(c, dmalloc(&sl.d_dlscal, 4));
+    ESVO_CUDA_TRY(c, cudaMallocHost((void**)&sl.h_dlscal, 8 * 8));
+    ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&sl.ev_dl, cudaEventDisableTiming));
+  }
+  if (!c->s_copy) ESVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+  {
+    StreamScope sc(c, c->s_fuse);   // right behind this frame's fusion, before the next frame resets the map
+    int rc = map_gather_async(c, sl.d_dl, sl.d_dl_keys, sl.d_dlscal, sl.h_dlscal);
+    if (rc) return rc;
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_counters, sl.d_counters, kCounters * 8, cudaMemcpyDeviceToHost, c->s_fuse));
+    ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_dl, c->s_fuse));
+  }
+  sl.dl_ticket = (int64_t)c->frame_no - 1;
+  if (ticket_out) *ticket_out = sl.dl_ticket;
+  return ESVO_OK;
+}
+ESVO_API int esvo_results_end(esvo_ctx* c, int64_t ticket, esvo_depth_point* out, size_t* n, uint64_t counters[8]) {
+  CHECK_CTX(c);
+  if (!n || ticket < 0) return ESVO_ERR_INVALID_ARG;
+  SlotBufs& sl = c->slots[(int)(ticket % c->depth)];
+  if (sl.dl_ticket != ticket) { c->set_error("esvo_results_end: unknown ticket"); return ESVO_ERR_STATE; }
+  ESVO_CUDA_TRY(c, cudaEventSynchronize(sl.ev_dl));
+  const size_t cnt = (size_t)sl.h_dlscal[1];
+  if (counters) {
+    counters[0] = sl.n_ev; counters[1] = sl.h_counters[1]; counters[2] = sl.h_counters[2]; counters[3] = sl.h_counters[3];
+    counters[4] = sl.h_dlscal[4]; counters[5] = sl.h_counters[5]; counters[6] = sl.h_counters[6]; counters[7] = sl.h_dlscal[6];
+  }
+  if (cnt > *n) { *n = cnt; return ESVO_ERR_CAPACITY; }
+  const size_t need = cnt * (sizeof(esvo_depth_point) + 8);
+  if (need > sl.h_dl_bytes) {
+    if (sl.h_dl) cudaFreeHost(sl.h_dl);
+    sl.h_dl_bytes = std::max<size_t>(need * 2, 1 << 20);
+    ESVO_CUDA_TRY(c, cudaMallocHost(&sl.h_dl, sl.h_dl_bytes));
+  }
+  esvo_depth_point* hp = (esvo_depth_point*)sl.h_dl;
+  unsigned long long* hk = (unsigned long long*)(hp + cnt);
+  if (cnt) {
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(hp, sl.d_dl, cnt * sizeof(esvo_depth_point), cudaMemcpyDeviceToHost, c->s_copy));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(hk, sl.d_dl_keys, cnt * 8, cudaMemcpyDeviceToHost, c->s_copy));
+    ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
+  }
+  // host marshalling: restore the SmartGrid list order (creation sequence)
+  std::vector<uint32_t> ord(cnt);
+  for (size_t i = 0; i < cnt; ++i) ord[i] = (uint32_t)i;
+  std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return hk[a] < hk[b]; });
+  for (size_t i = 0; i < cnt; ++i) out[i] = hp[ord[i]];
+  *n = cnt;
+  sl.dl_ticket = -1;
   return ESVO_OK;
 }
 ESVO_API uint64_t esvo_debug_counter(esvo_ctx* c, int idx) { return (c && idx >= 0 && idx < kCounters) ? c->h_counters[idx] : 0; }

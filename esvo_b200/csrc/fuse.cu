@@ -47,6 +47,8 @@ struct MapState {
   unsigned long long* d_dl_keys = nullptr;
   unsigned long long* d_scal = nullptr;  // [0] n_fusions, [1] download count
   unsigned long long* h_scal = nullptr;
+  double* h_T_ring = nullptr;            // pinned, 8 x 32 doubles: frame poses uploaded without a host sync
+  unsigned ring_idx = 0;
 };
 
 template <class T> static cudaError_t dm(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
@@ -362,6 +364,7 @@ int fuse_alloc(Ctx* c) {
   ESVO_CUDA_TRY(c, dm(&ms->d_dl, npix)); ESVO_CUDA_TRY(c, dm(&ms->d_dl_keys, npix));
   ESVO_CUDA_TRY(c, dm(&ms->d_scal, 4));
   ESVO_CUDA_TRY(c, cudaMallocHost((void**)&ms->h_scal, 4 * 8));
+  ESVO_CUDA_TRY(c, cudaMallocHost((void**)&ms->h_T_ring, 8 * 32 * 8));
   ESVO_CUDA_TRY(c, cudaMemset(M.exists, 0, npix));
   ESVO_CUDA_TRY(c, cudaMemset(ms->head, 0xff, npix * 4));
   ESVO_CUDA_TRY(c, cudaMemset(ms->d_scal, 0, 4 * 8));
@@ -379,6 +382,7 @@ void fuse_free(Ctx* c) {
                 ms->head, ms->next, ms->d_T_frame_world, ms->d_dl, ms->d_dl_keys, ms->d_scal};
   for (void* p : ps) if (p) cudaFree(p);
   if (ms->h_scal) cudaFreeHost(ms->h_scal);
+  if (ms->h_T_ring) cudaFreeHost(ms->h_T_ring);
   delete ms;
   c->map = nullptr;
 }
@@ -395,9 +399,10 @@ int fuse_reset_map(Ctx* c, const double T[16]) {
   I[15] = 1;
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) I[i * 4 + j] = T[j * 4 + i];
   for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += I[i * 4 + k] * T[k * 4 + 3]; I[i * 4 + 3] = -s; }
-  // pageable host source: cudaMemcpyAsync returns after staging, safe to reuse the members
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(ms->d_T_frame_world, ms->T_frame_world, 128, cudaMemcpyHostToDevice, c->stream));
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(ms->d_T_frame_world + 16, ms->T_world_frame, 128, cudaMemcpyHostToDevice, c->stream));
+  // pinned ring (8 frames deep, far more than the pipeline depth) so that the upload never blocks the host
+  double* hp = ms->h_T_ring + 32 * (ms->ring_idx++ & 7);
+  std::memcpy(hp, ms->T_frame_world, 128); std::memcpy(hp + 16, ms->T_world_frame, 128);
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(ms->d_T_frame_world, hp, 256, cudaMemcpyHostToDevice, c->stream));
   ms->seq_base = 0; ms->staged = 0;
   return ESVO_OK;
 }
@@ -470,6 +475,21 @@ int map_regularize(Ctx* c) {
                                                               c->prm.reg_min_close_neighbours);
   map_regularize_commit_kernel<<<div_up(npix, 256), 256, 0, c->stream>>>(npix, c->map->m);
   c->launches += 2;
+  return ESVO_OK;
+}
+
+// Enqueue (on c->stream) the compaction of the current map into caller-provided device buffers and the
+// D2H of its scalars: h_scal8[1] = element count, h_scal8[4] = n_fusions, h_scal8[6] = map size.
+int map_gather_async(Ctx* c, esvo_depth_point* d_out, unsigned long long* d_keys, unsigned long long* d_scal4,
+                     unsigned long long* h_scal8) {
+  MapState* ms = c->map;
+  const int npix = c->dc.W * c->dc.H, B = 128;
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(d_scal4, 0, 32, c->stream));
+  map_gather_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->d_T_frame_world + 16, d_out, d_keys, d_scal4);
+  c->launches += 1;
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(h_scal8, d_scal4, 32, cudaMemcpyDeviceToHost, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(h_scal8 + 4, ms->d_scal, 32, cudaMemcpyDeviceToHost, c->stream));
+  ESVO_CUDA_TRY(c, cudaGetLastError());
   return ESVO_OK;
 }
 

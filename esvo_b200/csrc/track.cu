@@ -718,6 +718,7 @@ ESVO_API int esvo_track_reset(esvo_ctx* c, float* ref_xyz, size_t n, const doubl
                               const uint8_t* ts_left) {
   CHECK_CTX(c);
   if (!ref_xyz || !Twr || !Twc) return ESVO_ERR_INVALID_ARG;
+  if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }
   const esvo_params& p = c->prm;
   if (p.trk_patch_size_x != 1 || p.trk_patch_size_y != 1) { c->set_error("tracking patch must be 1x1 (as in every shipped cfg)"); return ESVO_ERR_UNSUPPORTED; }
   if (p.trk_batch_size > TRK_MAXB || p.trk_batch_size < 6) { c->set_error("BATCH_SIZE must be in [6,1024]"); return ESVO_ERR_UNSUPPORTED; }
@@ -730,7 +731,7 @@ ESVO_API int esvo_track_reset(esvo_ctx* c, float* ref_xyz, size_t n, const doubl
   if (ts_left) ESVO_CUDA_TRY(c, cudaMemcpy2DAsync(d.ts, dc.pitch, ts_left, dc.W, dc.W, dc.H, cudaMemcpyHostToDevice, c->stream));
   else {
     if (!c->ts[0].built) { c->set_error("ts_left == NULL but no time surface was built for camera 0"); return ESVO_ERR_STATE; }
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(d.ts, c->ts[0].img_out, (size_t)dc.pitch * dc.H, cudaMemcpyDeviceToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(d.ts, c->ts[0].last_img, (size_t)dc.pitch * dc.H, cudaMemcpyDeviceToDevice, c->stream));
   }
   // setProblem (:24-68): R_, t_ from T_ref_left = T_world_ref^-1 * T_world_left
   double inv[16], Trl[16];

@@ -190,16 +190,18 @@ int ts_reset_state(Ctx* c, int cam) {
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.max_t, &mn, 8, cudaMemcpyHostToDevice, c->stream));
   ESVO_CUDA_TRY(c, cudaMemsetAsync(s.img_out, 0, (size_t)c->dc.pitch * c->dc.H, c->stream));
   ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  s.log_n = 0; s.log_base = 0; s.built = false;
+  s.log_n = 0; s.log_base = 0; s.built = false; s.last_img = s.img_out;
   return ESVO_OK;
 }
 
 int ts_alloc(Ctx* c, int cam) {
   TsState& s = c->ts[cam];
   const size_t npix = (size_t)c->dc.W * c->dc.H;
-  s.log_cap = (size_t)1 << 22;  // 4 Mi events resident per camera (52 MiB); older ones fold into base grids
+  s.log_cap = (size_t)1 << 22;  // 4 Mi events resident per camera (2 x 52 MiB, ping-pong); older ones fold into base grids
   ESVO_CUDA_TRY(c, dmalloc(&s.ex, s.log_cap)); ESVO_CUDA_TRY(c, dmalloc(&s.ey, s.log_cap));
   ESVO_CUDA_TRY(c, dmalloc(&s.et, s.log_cap)); ESVO_CUDA_TRY(c, dmalloc(&s.ep, s.log_cap));
+  ESVO_CUDA_TRY(c, dmalloc(&s.ex2, s.log_cap)); ESVO_CUDA_TRY(c, dmalloc(&s.ey2, s.log_cap));
+  ESVO_CUDA_TRY(c, dmalloc(&s.et2, s.log_cap)); ESVO_CUDA_TRY(c, dmalloc(&s.ep2, s.log_cap));
   ESVO_CUDA_TRY(c, dmalloc(&s.cur_idx, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.cur_t, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.cur_pol, npix));
   ESVO_CUDA_TRY(c, dmalloc(&s.base_idx, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.base_t, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.base_pol, npix));
   ESVO_CUDA_TRY(c, dmalloc(&s.tmp_idx, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.tmp_t, npix)); ESVO_CUDA_TRY(c, dmalloc(&s.tmp_pol, npix));
@@ -215,18 +217,21 @@ int ts_alloc(Ctx* c, int cam) {
 }
 void ts_free(Ctx* c, int cam) {
   TsState& s = c->ts[cam];
-  void* ps[] = {s.ex, s.ey, s.et, s.ep, s.cur_idx, s.cur_t, s.cur_pol, s.base_idx, s.base_t, s.base_pol, s.tmp_idx,
+  void* ps[] = {s.ex2, s.ey2, s.et2, s.ep2, s.ex, s.ey, s.et, s.ep, s.cur_idx, s.cur_t, s.cur_pol, s.base_idx, s.base_t, s.base_pol, s.tmp_idx,
                 s.tmp_t, s.tmp_pol, s.cnt, s.out_idx, s.img_med, s.img_out, s.map1, s.map2, s.scalars, s.max_t};
   for (void* p : ps) if (p) cudaFree(p);
   s = TsState();
 }
 
-// Evict the oldest half of the log into the base grids when the next push would overflow.
+// When the next push would overflow the resident log, fold the oldest events into the base grids and
+// move the most recent ones to the alternate buffer set (ping-pong).  Everything is enqueued on the
+// ctx stream: no allocation, no host synchronisation.
 static int ts_make_room(Ctx* c, int cam, size_t n_new) {
   TsState& s = c->ts[cam];
-  if (n_new > s.log_cap) { c->set_error("event batch larger than the resident log"); return ESVO_ERR_CAPACITY; }
+  if (n_new > s.log_cap / 2) { c->set_error("event batch larger than half the resident log"); return ESVO_ERR_CAPACITY; }
   if (s.log_n + n_new <= s.log_cap) return ESVO_OK;
-  size_t drop = std::max(s.log_n / 2, s.log_n + n_new - s.log_cap);
+  const size_t keep = std::min(s.log_n, s.log_cap / 4);
+  const size_t drop = s.log_n - keep;
   const int B = 256;
   unsigned g = (unsigned)((drop + B - 1) / B);
   ts_scatter_kernel<<<g, B, 0, c->stream>>>(s.ex, s.ey, s.et, drop, s.log_base, c->dc.W, c->dc.H, (long long*)s.base_idx,
@@ -234,20 +239,11 @@ static int ts_make_room(Ctx* c, int cam, size_t n_new) {
   ts_scatter_fix_kernel<<<g, B, 0, c->stream>>>(s.ex, s.ey, s.et, s.ep, drop, s.log_base, c->dc.W, c->dc.H,
                                                 (const long long*)s.base_idx, (long long*)s.base_t, s.base_pol, nullptr);
   c->launches += 2;
-  size_t keep = s.log_n - drop;
-  // compaction through the (free) tail is not possible in place for overlapping ranges: stage via tmp copies
-  uint16_t* tx; uint16_t* ty; int64_t* tt; uint8_t* tp;
-  ESVO_CUDA_TRY(c, dmalloc(&tx, keep)); ESVO_CUDA_TRY(c, dmalloc(&ty, keep)); ESVO_CUDA_TRY(c, dmalloc(&tt, keep)); ESVO_CUDA_TRY(c, dmalloc(&tp, keep));
-  cudaMemcpyAsync(tx, s.ex + drop, keep * 2, cudaMemcpyDeviceToDevice, c->stream);
-  cudaMemcpyAsync(ty, s.ey + drop, keep * 2, cudaMemcpyDeviceToDevice, c->stream);
-  cudaMemcpyAsync(tt, s.et + drop, keep * 8, cudaMemcpyDeviceToDevice, c->stream);
-  cudaMemcpyAsync(tp, s.ep + drop, keep, cudaMemcpyDeviceToDevice, c->stream);
-  cudaMemcpyAsync(s.ex, tx, keep * 2, cudaMemcpyDeviceToDevice, c->stream);
-  cudaMemcpyAsync(s.ey, ty, keep * 2, cudaMemcpyDeviceToDevice, c->stream);
-  cudaMemcpyAsync(s.et, tt, keep * 8, cudaMemcpyDeviceToDevice, c->stream);
-  cudaMemcpyAsync(s.ep, tp, keep, cudaMemcpyDeviceToDevice, c->stream);
-  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  cudaFree(tx); cudaFree(ty); cudaFree(tt); cudaFree(tp);
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ex2, s.ex + drop, keep * 2, cudaMemcpyDeviceToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ey2, s.ey + drop, keep * 2, cudaMemcpyDeviceToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.et2, s.et + drop, keep * 8, cudaMemcpyDeviceToDevice, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ep2, s.ep + drop, keep, cudaMemcpyDeviceToDevice, c->stream));
+  std::swap(s.ex, s.ex2); std::swap(s.ey, s.ey2); std::swap(s.et, s.et2); std::swap(s.ep, s.ep2);
   s.log_base += (int64_t)drop; s.log_n = keep;
   return ESVO_OK;
 }
@@ -327,6 +323,7 @@ int ts_run_build(Ctx* c, int cam, int64_t T) {
   c->prof_end(pe);
   ESVO_CUDA_TRY(c, cudaGetLastError());
   s.built = true;
+  s.last_img = s.img_out;
   return ESVO_OK;
 }
 

@@ -264,6 +264,19 @@ ESVO_API int esvo_stage_mapping_inputs(esvo_ctx* ctx, const uint16_t* ex, const 
 ESVO_API int esvo_run_mapping(esvo_ctx* ctx);
 ESVO_API int esvo_fetch_mapping_counters(esvo_ctx* ctx, uint64_t counters_out[8]);
 ESVO_API int esvo_sync(esvo_ctx* ctx);
+/* Software pipelining of consecutive mapping frames (1 = strictly sequential, the default; up to 8).
+ * With depth S the frames issued through esvo_set_ts_pair_dev / esvo_stage_mapping_inputs(_dev) /
+ * esvo_run_mapping rotate over S buffer sets and CUDA streams so that the serial tail of one frame's
+ * LM kernel overlaps with the next frames; results are identical to depth 1. */
+ESVO_API int esvo_set_pipeline_depth(esvo_ctx* ctx, int depth);
+/* Asynchronous result hand-off for pipelined operation.  esvo_results_begin enqueues, right behind the
+ * frame just issued with esvo_run_mapping, the compaction of its fused map and the read-back of its
+ * counters; esvo_results_end(ticket) waits for that frame only, copies the map out in element-list order
+ * (same content as esvo_map_download) and fills counters_out[8] (same layout as esvo_mapping_at_time).
+ * Each pipeline slot holds one pending ticket: collect frame j before issuing frame j + depth. */
+ESVO_API int esvo_results_begin(esvo_ctx* ctx, int64_t* ticket_out);
+ESVO_API int esvo_results_end(esvo_ctx* ctx, int64_t ticket, esvo_depth_point* out, size_t* n,
+                              uint64_t* counters_out);
 /* Device-pointer forms (suffix _dev): the arrays are CUDA device pointers on the ctx's device, i.e.
  * the inputs are already resident in HBM; work is enqueued on the ctx stream, nothing is synchronised.
  * esvo_set_ts_pair_dev hands the images of the last two esvo_run_ts_build calls to the mapper. */

@@ -239,3 +239,71 @@ def test_tracking_too_few_points(oracle_lib, product_lib):
     cloud = np.zeros((10, 3), np.float32); cloud[:, 2] = 1
     for be in (o, g):
         assert be.track_reset(cloud.copy(), np.eye(4), np.eye(4), tl) == 1
+
+
+@pytest.mark.parametrize("depth", [1, 3])
+def test_pipelined_frames_match_oracle(oracle_lib, product_lib, depth):
+    """Software-pipelined frames (esvo_set_pipeline_depth + esvo_results_begin/end) give the same per-frame
+    maps and counters as the sequential oracle."""
+    def tw(p):
+        p.max_num_fusion_frames = 3
+    o, g = make_backends("hkust", oracle_lib, product_lib, tweak=tw)
+    g.set_pipeline_depth(depth)
+    frames = [scenario("hkust", n_seeds=600, t_ts=t) for t in (0.50, 0.55, 0.60, 0.65, 0.70)]
+    expected = []
+    for s in frames:
+        tl, tr = build_ts_pair(o, s)
+        o.ts_reset(0); o.ts_reset(1)
+        o.set_ts_pair(tl, tr, s["T_world_left"])
+        sd = s["seeds"]
+        c = o.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+        expected.append((c, o.map_download(), tl, tr))
+    tickets, got = [], []
+    for k, s in enumerate(frames):
+        if len(tickets) >= max(1, depth - 1):
+            m, c = g.results_end(tickets.pop(0)); got.append((c, m.copy()))
+        # device-resident TS hand-off: build the pair on the GPU from the raw events
+        g.ts_reset(0); g.ts_reset(1)
+        for cam, side in ((0, "left"), (1, "right")):
+            e = s[side]
+            g.stage_ts_events(cam, e["x"], e["y"], e["t"], e["p"])
+            g.run_ts_build(cam, s["t_ts_ns"])
+        T = np.ascontiguousarray(s["T_world_left"], np.float64)
+        import ctypes as C
+        g._call("set_ts_pair_dev", [C.POINTER(C.c_double)], T.ctypes.data_as(C.POINTER(C.c_double)))
+        sd = s["seeds"]
+        g.stage_mapping_inputs(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+        g.run_mapping()
+        tickets.append(g.results_begin())
+    while tickets:
+        m, c = g.results_end(tickets.pop(0)); got.append((c, m.copy()))
+    assert len(got) == len(expected)
+    for k, ((co, mo, _, _), (cg, mg)) in enumerate(zip(expected, got)):
+        for key in ("n_events", "n_seeds", "n_solved", "n_culled", "bm_evals", "n_fusions", "map_size"):
+            assert co[key] == cg[key], (k, key, co, cg)
+        assert mo.size == mg.size
+        assert np.array_equal(mo["row"], mg["row"]) and np.array_equal(mo["col"], mg["col"])
+        r = rel(mg["inv_depth"], mo["inv_depth"])
+        assert (r < 1e-4).mean() > 0.995 and np.median(r) < 1e-7
+
+
+def test_time_surface_log_eviction(oracle_lib, product_lib):
+    """Pushing more events than the resident log holds folds the oldest ones into the base grids; both the
+    fast path (T newer than everything) and the general path (T inside the resident part) stay bit-exact."""
+    o, g = make_backends("hkust", oracle_lib, product_lib)
+    rng = np.random.default_rng(5)
+    n_batch, n_batches = 1_500_000, 5            # 7.5 M events > 4 Mi resident
+    t0 = 1_000_000_000
+    for b in range(n_batches):
+        x = rng.integers(0, 346, n_batch).astype(np.uint16); y = rng.integers(0, 260, n_batch).astype(np.uint16)
+        # leave some pixels untouched after the first batch so that their value must come from the base grids
+        if b > 0:
+            x[x < 40] += 40
+        t = (t0 + (b * n_batch + np.arange(n_batch)) * 40).astype(np.int64); p = rng.integers(0, 2, n_batch).astype(np.uint8)
+        for be in (o, g):
+            be.ts_push_events(0, x, y, t, p)
+    t_end = int(t[-1])
+    for T in (t_end + 1000, t_end - 200_000 * 40, t_end - 900_000 * 40):
+        io, to = o.ts_build(0, T); ig, tg = g.ts_build(0, T)
+        assert np.array_equal(io, ig), f"T={T}: {(io != ig).sum()} idx mismatches"
+        assert np.array_equal(to, tg)
