@@ -122,7 +122,8 @@ def run_ours(args, rank, world, local_rank):
     t_wait = time.time()
     while not sampler.rows and time.time() - t_wait < 15:     # nvidia-smi start-up is over once the first row arrives
         time.sleep(0.05)
-    base = make_workload(seed=10 + rank)
+    from esvo_b200 import dist as _ed
+    base = make_workload(seed=_ed.stream_seed(rank))
     K, Wm = args.steps, args.warmup
     NP = prm.max_num_fusion_frames
     allf = [shifted(base, k) for k in range(NP + 2 * (K + Wm) + 2)]
@@ -279,17 +280,12 @@ def run_ours(args, rank, world, local_rank):
     # TS-only rate (second half of the metric): resident events -> rectified u8 TS, both cameras per step
     ts_frames_per_s = 2 * K / (ms[0] / 1e3) if ms[0] > 0 else None
 
-    # max over ranks
-    tot = torch.tensor([total_ms, e2e_s * 1e3, float(evals_step), float(e2e_evals)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        import torch.distributed as dist
-        mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        total_ms, e2e_ms = float(mx[0]), float(mx[1])
-        evals_all, e2e_evals_all = float(sm[2]), float(sm[3])
-    else:
-        e2e_ms = e2e_s * 1e3
-        evals_all, e2e_evals_all = float(evals_step), float(e2e_evals)
+    # timing = max over ranks, work = sum over ranks, one result record per stream (esvo_b200/dist.py)
+    from esvo_b200 import dist as edist
+    m_last = g.map_download()
+    rec = edist.make_record(edist.stream_seed(rank), K, ce, edist.map_checksum(m_last))
+    total_ms, evals_all, records = edist.reduce_and_gather(total_ms, float(evals_step), rec, device="cuda")
+    e2e_ms, e2e_evals_all, _ = edist.reduce_and_gather(e2e_s * 1e3, float(e2e_evals), rec, device="cuda")
     if rank != 0:
         return
     peak, peak_kind = load_peaks()
@@ -336,6 +332,7 @@ def run_ours(args, rank, world, local_rank):
                      "n_seeds": ctr["n_seeds"], "n_solved": ctr["n_solved"], "n_culled": ctr["n_culled"],
                      "n_fusions": ctr["n_fusions"], "map_size": ctr["map_size"]},
         "wall_s_timed_region": t_wall,
+        "streams": [dict(zip(edist.RECORD_FIELDS, [float(v) for v in r])) for r in records],
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_leg(base, sample_steps=3)
