@@ -1,0 +1,259 @@
+// esvo_b200 -- C++ host shim over the C ABI (include/esvo_b200.h).
+//
+// ROS-free mirror of the reference's class surface for the hot path, so that code written against
+// esvo_core::core::{EventBM, DepthProblemSolver, DepthFusion, RegProblemSolverLM} and
+// esvo_time_surface::TimeSurface keeps its shape: same class and method names, same argument meaning,
+// same "bool return for data-dependent failure, no exceptions" convention
+// (reference: esvo_core/include/esvo_core/core/*.h, esvo_time_surface/include/esvo_time_surface/TimeSurface.h).
+// ROS / Eigen / OpenCV types are replaced by plain structs: ros::Time -> int64 ns, Transformation -> row-major
+// double[16], cv::Mat mono8 -> uint8_t*, dvs_msgs::Event -> esvo::Event.  Header-only; link with libesvo_b200.so.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../esvo_b200.h"
+
+namespace esvo {
+
+struct Event { uint16_t x, y; int64_t ts; bool polarity; };            // dvs_msgs::Event
+using Pose = std::array<double, 16>;                                    // Transformation (T_world_cam, row-major)
+using StampTransformationMap = std::vector<std::pair<int64_t, Pose>>;   // sorted by stamp
+using EventMatchPair = esvo_seed;                                       // core::EventMatchPair
+using DepthPoint = esvo_depth_point;                                    // container::DepthPoint
+
+// container::CameraSystem + the parameter yaml of one node: owns the esvo_ctx of one event stream / GPU.
+class CameraSystem {
+ public:
+  using Ptr = std::shared_ptr<CameraSystem>;
+  CameraSystem(const esvo_calib& left, const esvo_calib& right, const esvo_params& params, int device = 0) {
+    int st = 0;
+    ctx_ = esvo_create(device, &left, &right, &params, &st);
+    if (!ctx_) throw std::runtime_error("esvo_create failed with status " + std::to_string(st) + " (no CPU fallback)");
+    params_ = params; width_ = left.width; height_ = left.height;
+    double d[4]; esvo_get_derived(ctx_, d); baseline_ = d[0];
+  }
+  ~CameraSystem() { esvo_destroy(ctx_); }
+  CameraSystem(const CameraSystem&) = delete;
+  CameraSystem& operator=(const CameraSystem&) = delete;
+  esvo_ctx* ctx() const { return ctx_; }
+  const esvo_params& params() const { return params_; }
+  int width_ = 0, height_ = 0;
+  double baseline_ = 0;
+ private:
+  esvo_ctx* ctx_ = nullptr;
+  esvo_params params_;
+};
+
+// container::TimeSurfaceObservation (stereo mono8 pair + pose); images are borrowed, not copied.
+struct TimeSurfaceObservation {
+  const uint8_t* left = nullptr;    // nullptr = "the image esvo_ts_build produced on the device"
+  const uint8_t* right = nullptr;
+  Pose tr_{};
+  size_t id_ = 0;
+  void setTransformation(const Pose& tr) { tr_ = tr; }
+};
+using StampedTimeSurfaceObs = std::pair<int64_t, TimeSurfaceObservation>;
+
+}  // namespace esvo
+
+namespace esvo_time_surface {
+// esvo_time_surface::TimeSurface (TimeSurface.h:98-170) without the ROS node handle: the three callbacks
+// become plain methods, the published image is returned to the caller.
+class TimeSurface {
+ public:
+  TimeSurface(esvo::CameraSystem::Ptr cs, int cam) : cs_(std::move(cs)), cam_(cam) {}
+  // eventsCallback (TimeSurface.cpp:403-425)
+  bool eventsCallback(const std::vector<esvo::Event>& events) {
+    x_.resize(events.size()); y_.resize(events.size()); t_.resize(events.size()); p_.resize(events.size());
+    for (size_t i = 0; i < events.size(); ++i) { x_[i] = events[i].x; y_[i] = events[i].y; t_[i] = events[i].ts; p_[i] = events[i].polarity; }
+    return esvo_ts_push_events(cs_->ctx(), cam_, x_.data(), y_.data(), t_.data(), p_.data(), events.size()) == ESVO_OK;
+  }
+  // syncCallback -> createTimeSurfaceAtTime (TimeSurface.cpp:52-152,293-311); time_surface_out: H*W mono8 or nullptr
+  bool createTimeSurfaceAtTime(int64_t external_sync_time_ns, uint8_t* time_surface_out) {
+    return esvo_ts_build(cs_->ctx(), cam_, external_sync_time_ns, nullptr, time_surface_out) == ESVO_OK;
+  }
+  void clearEventQueue() { esvo_ts_reset(cs_->ctx(), cam_); }
+ private:
+  esvo::CameraSystem::Ptr cs_;
+  int cam_;
+  std::vector<uint16_t> x_, y_;
+  std::vector<int64_t> t_;
+  std::vector<uint8_t> p_;
+};
+}  // namespace esvo_time_surface
+
+namespace esvo_core {
+namespace core {
+using esvo::CameraSystem;
+using esvo::DepthPoint;
+using esvo::EventMatchPair;
+
+// core::EventBM (EventBM.h:27-60).  Patch size / disparity range / step / threshold come from the params the
+// CameraSystem was created with (the reference passes them to resetParameters from the same yaml).
+class EventBM {
+ public:
+  explicit EventBM(CameraSystem::Ptr camSysPtr) : camSysPtr_(std::move(camSysPtr)) {}
+  void createMatchProblem(esvo::StampedTimeSurfaceObs* pStampedTsObs, esvo::StampTransformationMap* pSt_map,
+                          std::vector<esvo::Event*>* pvEventsPtr) {
+    pStampedTsObs_ = pStampedTsObs; pSt_map_ = pSt_map;
+    ex_.clear(); ey_.clear(); et_.clear();
+    for (auto* e : *pvEventsPtr) { ex_.push_back(e->x); ey_.push_back(e->y); et_.push_back(e->ts); }
+  }
+  void match_all_HyperThread(std::vector<EventMatchPair>& vEMP) {
+    vEMP.clear();
+    if (!pStampedTsObs_ || !pSt_map_) return;
+    const auto& obs = pStampedTsObs_->second;
+    if (esvo_set_ts_pair(camSysPtr_->ctx(), obs.left, obs.right, obs.tr_.data()) != ESVO_OK) return;
+    std::vector<int64_t> pt; std::vector<double> poses;
+    for (auto& st : *pSt_map_) { pt.push_back(st.first); poses.insert(poses.end(), st.second.begin(), st.second.end()); }
+    vEMP.resize(ex_.size());
+    size_t n = vEMP.size();
+    if (esvo_bm_match(camSysPtr_->ctx(), ex_.data(), ey_.data(), et_.data(), ex_.size(), pt.data(), poses.data(), pt.size(),
+                      vEMP.data(), &n, &n_evals_) != ESVO_OK) n = 0;
+    vEMP.resize(n);
+  }
+  void match_all_SingleThread(std::vector<EventMatchPair>& vEMP) { match_all_HyperThread(vEMP); }
+  uint64_t n_evals_ = 0;
+ private:
+  CameraSystem::Ptr camSysPtr_;
+  esvo::StampedTimeSurfaceObs* pStampedTsObs_ = nullptr;
+  esvo::StampTransformationMap* pSt_map_ = nullptr;
+  std::vector<uint16_t> ex_, ey_;
+  std::vector<int64_t> et_;
+};
+
+enum DepthProblemType { ANALYTICAL, NUMERICAL };
+// core::DepthProblemSolver (DepthProblemSolver.h:35-60)
+class DepthProblemSolver {
+ public:
+  DepthProblemSolver(CameraSystem::Ptr& camSysPtr, DepthProblemType dpType = NUMERICAL) : camSysPtr_(camSysPtr), dpType_(dpType) {}
+  void solve(std::vector<EventMatchPair>* pvEMP, esvo::StampedTimeSurfaceObs* pStampedTsObs, std::vector<DepthPoint>& vdp) {
+    vdp.clear();
+    if (dpType_ != NUMERICAL || !pvEMP || pvEMP->empty()) return;   // the reference exit(-1)s on ANALYTICAL
+    const auto& obs = pStampedTsObs->second;
+    if (esvo_set_ts_pair(camSysPtr_->ctx(), obs.left, obs.right, obs.tr_.data()) != ESVO_OK) return;
+    vdp.resize(pvEMP->size());
+    size_t n = vdp.size();
+    if (esvo_depth_solve(camSysPtr_->ctx(), pvEMP->data(), pvEMP->size(), vdp.data(), &n, &n_evals_) != ESVO_OK) n = 0;
+    vdp.resize(n);
+  }
+  void pointCulling(std::vector<DepthPoint>& vdp, double std_variance_threshold, double cost_threshold,
+                    double invDepth_min_range, double invDepth_max_range) {
+    size_t n = vdp.size();
+    if (esvo_depth_cull(camSysPtr_->ctx(), vdp.data(), &n, std_variance_threshold, cost_threshold, invDepth_min_range,
+                        invDepth_max_range) == ESVO_OK)
+      vdp.resize(n);
+  }
+  DepthProblemType getProblemType() { return dpType_; }
+  uint64_t n_evals_ = 0;
+ private:
+  CameraSystem::Ptr camSysPtr_;
+  DepthProblemType dpType_;
+};
+
+// container::DepthFrame: the fused map lives on the device inside the ctx; this handle carries its pose.
+struct DepthFrame {
+  using Ptr = std::shared_ptr<DepthFrame>;
+  esvo::Pose T_world_frame_{};
+  size_t id_ = 0;
+  bool fresh_ = true;   // a newly constructed DepthFrame starts from an empty map (esvo_Mapping.cpp:268-272)
+  void setTransformation(const esvo::Pose& T) { T_world_frame_ = T; }
+  void setId(size_t id) { id_ = id; }
+};
+
+// core::DepthFusion (DepthFusion.h:21-59)
+class DepthFusion {
+ public:
+  explicit DepthFusion(CameraSystem::Ptr& camSysPtr) : camSysPtr_(camSysPtr) {}
+  int update(std::vector<DepthPoint>& dp_obs, DepthFrame::Ptr& df, int fusion_radius) {
+    int nf = 0;
+    if (esvo_fuse(camSysPtr_->ctx(), dp_obs.data(), dp_obs.size(), df->T_world_frame_.data(), fusion_radius, df->fresh_ ? 1 : 0,
+                  &nf) != ESVO_OK)
+      return 0;
+    df->fresh_ = false;
+    return nf;
+  }
+  // DepthMap::clean (SmartGrid.h:222-243) and the element list, exposed here because the map is ctx-resident
+  void clean(double var_threshold, double age_threshold, double range_max, double range_min) {
+    esvo_map_clean(camSysPtr_->ctx(), var_threshold, age_threshold, range_max, range_min);
+  }
+  void getElements(std::vector<DepthPoint>& out) {
+    out.resize((size_t)camSysPtr_->width_ * camSysPtr_->height_);
+    size_t n = out.size();
+    if (esvo_map_download(camSysPtr_->ctx(), out.data(), &n) != ESVO_OK) n = 0;
+    out.resize(n);
+  }
+ private:
+  CameraSystem::Ptr camSysPtr_;
+};
+
+// core::DepthRegularization (DepthRegularization.h:20)
+class DepthRegularization {
+ public:
+  explicit DepthRegularization(CameraSystem::Ptr& camSysPtr) : camSysPtr_(camSysPtr) {}
+  void apply() { esvo_map_regularize(camSysPtr_->ctx()); }
+ private:
+  CameraSystem::Ptr camSysPtr_;
+};
+
+// core::RefFrame / CurFrame (RegProblemLM.h:58-74)
+struct RefFrame { int64_t t_ = 0; std::vector<float> vPointXYZ_; /* n*3, world frame; permuted in place */ esvo::Pose tr_{}; };
+struct CurFrame { int64_t t_ = 0; const uint8_t* ts_left = nullptr; esvo::Pose tr_{}; size_t numEventsSinceLastObs_ = 0; };
+struct LM_statics { size_t nPoints_ = 0, nfev_ = 0, nIter_ = 0; };
+enum RegProblemType { REG_NUMERICAL, REG_ANALYTICAL };
+
+// core::RegProblemSolverLM (RegProblemSolverLM.h:37-50)
+class RegProblemSolverLM {
+ public:
+  RegProblemSolverLM(CameraSystem::Ptr& camSysPtr, RegProblemType rpType = REG_ANALYTICAL) : camSysPtr_(camSysPtr), rpType_(rpType) {}
+  bool resetRegProblem(RefFrame* ref, CurFrame* cur) {
+    cur_ = cur;
+    int rc = esvo_track_reset(camSysPtr_->ctx(), ref->vPointXYZ_.data(), ref->vPointXYZ_.size() / 3, ref->tr_.data(),
+                              cur->tr_.data(), cur->ts_left);
+    lmStatics_ = LM_statics();
+    return rc == ESVO_OK;   // 1 = not enough points in the local map -> the system re-initialises
+  }
+  bool solve_numerical() { return solve(0); }
+  bool solve_analytical() { return solve(1); }
+  LM_statics lmStatics_;
+ private:
+  bool solve(int analytical) {
+    esvo_lm_stats st{};
+    if (!cur_ || esvo_track_solve(camSysPtr_->ctx(), analytical, cur_->tr_.data(), &st) != ESVO_OK) return false;
+    lmStatics_.nPoints_ = (size_t)st.n_points; lmStatics_.nfev_ = (size_t)st.nfev; lmStatics_.nIter_ = (size_t)st.n_iter;
+    return true;
+  }
+  CameraSystem::Ptr camSysPtr_;
+  RegProblemType rpType_;
+  CurFrame* cur_ = nullptr;
+};
+
+}  // namespace core
+
+// esvo_core::esvo_Mapping::MappingAtTime (esvo_Mapping.cpp:261-399) as one call with device-resident hand-off.
+class esvo_Mapping {
+ public:
+  explicit esvo_Mapping(esvo::CameraSystem::Ptr cs) : cs_(std::move(cs)) {}
+  struct Counters { uint64_t n_events, n_seeds, n_solved, n_culled, n_fusions, bm_evals, lm_evals, map_size; };
+  bool MappingAtTime(const esvo::StampedTimeSurfaceObs& TS_obs, const std::vector<esvo::Event*>& vCloseEventsPtr_left,
+                     const esvo::StampTransformationMap& st_map, Counters* out = nullptr) {
+    const auto& obs = TS_obs.second;
+    if (esvo_set_ts_pair(cs_->ctx(), obs.left, obs.right, obs.tr_.data()) != ESVO_OK) return false;
+    std::vector<uint16_t> ex, ey; std::vector<int64_t> et, pt; std::vector<double> poses;
+    for (auto* e : vCloseEventsPtr_left) { ex.push_back(e->x); ey.push_back(e->y); et.push_back(e->ts); }
+    for (auto& st : st_map) { pt.push_back(st.first); poses.insert(poses.end(), st.second.begin(), st.second.end()); }
+    uint64_t c[8];
+    if (esvo_mapping_at_time(cs_->ctx(), ex.data(), ey.data(), et.data(), ex.size(), pt.data(), poses.data(), pt.size(), c) != ESVO_OK)
+      return false;
+    if (out) *out = Counters{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]};
+    return true;
+  }
+  void reset() { esvo_mapping_reset(cs_->ctx()); }
+ private:
+  esvo::CameraSystem::Ptr cs_;
+};
+}  // namespace esvo_core

@@ -21,8 +21,11 @@ def test_header_symbols_exported(product_lib, oracle_lib):
         assert hasattr(product_lib.lib, n), f"product library does not export {n}"
     # the oracle mirrors the compute entry points under its own prefix
     for n in names:
-        if n in ("esvo_stage_ts_events", "esvo_run_ts_build", "esvo_stage_mapping_inputs", "esvo_run_mapping",
-                 "esvo_fetch_mapping_counters", "esvo_sync", "esvo_stream", "esvo_launch_count", "esvo_last_error"):
+        # device-side plumbing has no CPU counterpart
+        if n.endswith("_dev") or n in ("esvo_stage_ts_events", "esvo_run_ts_build", "esvo_stage_mapping_inputs",
+                                       "esvo_run_mapping", "esvo_fetch_mapping_counters", "esvo_sync", "esvo_stream",
+                                       "esvo_launch_count", "esvo_last_error", "esvo_debug_counter", "esvo_profile",
+                                       "esvo_profile_read", "esvo_set_pipeline_depth", "esvo_results_begin", "esvo_results_end"):
             continue
         assert hasattr(oracle_lib.lib, n.replace("esvo_", "esvo_oracle_", 1)), n
 
