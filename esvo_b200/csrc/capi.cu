@@ -70,7 +70,7 @@ int map_alloc_inputs(Ctx* c, size_t n_ev, size_t n_poses) {
 
 #define SLOT_FIELDS(X) X(obs_l) X(obs_r) X(obs_ls) X(obs_rs) X(d_T_left_world) X(ev_cap) X(pose_cap) X(n_ev) X(n_poses) \
   X(d_ex) X(d_ey) X(d_et) X(d_pose_t) X(d_poses) X(bm) X(d_seeds) X(lm_flag) X(lm_res) X(lm_dbg) X(d_pts) X(d_counters) \
-  X(h_counters) X(h_pin)
+  X(h_counters) X(h_pin) X(map)
 void slot_save(Ctx* c) {
   SlotBufs& s = c->slots[c->cur];
 #define X(f) s.f = c->f;
@@ -104,13 +104,20 @@ int slot_alloc(Ctx* c, int i) {
   ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&s.ev_obs, cudaEventDisableTiming));
   ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&s.ev_free, cudaEventDisableTiming));
   ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&s.ev_pts, cudaEventDisableTiming));
+  ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&s.ev_fuse, cudaEventDisableTiming));
+  {  // the slot's own map / fusion staging
+    MapState* keep = c->map;
+    int rc = fuse_alloc(c);
+    s.map = c->map;
+    c->map = keep;
+    if (rc) return rc;
+  }
   s.allocated = true;
   return ESVO_OK;
 }
 int drain(Ctx* c) {
   if (c->s_ts) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_ts));
   for (int i = 0; i < kMaxSlots; ++i) if (c->slots[i].stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->slots[i].stream));
-  if (c->s_fuse) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_fuse));
   if (c->s_copy) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
   return ESVO_OK;
 }
@@ -190,11 +197,9 @@ ESVO_API int esvo_set_pipeline_depth(esvo_ctx* c, int depth) {
   slot_save(c);
   if (depth > 1) {
     if (c->s_ts == c->s_main) ESVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_ts, cudaStreamNonBlocking));
-    if (c->s_fuse == c->s_main) ESVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_fuse, cudaStreamNonBlocking));
     for (int i = 1; i < depth; ++i) if ((rc = slot_alloc(c, i))) return rc;
   } else {
     if (c->s_ts != c->s_main) { cudaStreamDestroy(c->s_ts); c->s_ts = c->s_main; }
-    if (c->s_fuse != c->s_main) { cudaStreamDestroy(c->s_fuse); c->s_fuse = c->s_main; }
   }
   c->depth = depth;
   c->frame_no = 0;
@@ -240,17 +245,15 @@ ESVO_API esvo_ctx* esvo_create(int device, const esvo_calib* left, const esvo_ca
   if (d.dmax >= d.dmin && (d.dmax - d.dmin) / d.step + 1 > 192 && d.step > 1) { delete c; return fail(ESVO_ERR_UNSUPPORTED); }
   auto bail = [&](int code) -> esvo_ctx* { esvo_destroy(c); return fail(code); };
   if (cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) != cudaSuccess) return bail(ESVO_ERR_CUDA);
-  c->stream = c->s_ts = c->s_fuse = c->s_main;
+  c->stream = c->s_ts = c->s_main;
   c->slots[0].stream = c->s_main;
   const size_t npix = (size_t)d.W * d.H;
   if (slot_alloc(c, 0)) return bail(ESVO_ERR_CUDA);
   slot_load(c, 0);
-  if (cudaEventCreateWithFlags(&c->ev_fuse_done, cudaEventDisableTiming) != cudaSuccess) return bail(ESVO_ERR_CUDA);
   if (dmalloc(&c->d_lut, 2 * npix) || dmalloc(&c->d_mask, npix)) return bail(ESVO_ERR_CUDA);
   for (int cam = 0; cam < 2; ++cam) if (ts_alloc(c, cam)) return bail(ESVO_ERR_CUDA);
   if (upload_tables(c)) return bail(ESVO_ERR_CUDA);
   if (map_alloc_inputs(c, 16384, 512)) return bail(ESVO_ERR_CUDA);
-  if (fuse_alloc(c)) return bail(ESVO_ERR_CUDA);
   if (track_alloc(c)) return bail(ESVO_ERR_CUDA);
   if (status_out) *status_out = ESVO_OK;
   return c;
@@ -263,7 +266,7 @@ ESVO_API void esvo_destroy(esvo_ctx* c) {
   if (c->slots[0].allocated) slot_save(c);
   c->stream = c->s_main;
   for (int cam = 0; cam < 2; ++cam) ts_free(c, cam);
-  fuse_free(c);
+  for (int i = 0; i < kMaxSlots; ++i) if (c->slots[i].map) { c->map = c->slots[i].map; fuse_free(c); c->slots[i].map = nullptr; }
   track_free(c);
   if (c->d_lut) cudaFree(c->d_lut);
   if (c->d_mask) cudaFree(c->d_mask);
@@ -278,6 +281,7 @@ ESVO_API void esvo_destroy(esvo_ctx* c) {
     if (s.ev_obs) cudaEventDestroy(s.ev_obs);
     if (s.ev_free) cudaEventDestroy(s.ev_free);
     if (s.ev_pts) cudaEventDestroy(s.ev_pts);
+    if (s.ev_fuse) cudaEventDestroy(s.ev_fuse);
     if (s.ev_dl) cudaEventDestroy(s.ev_dl);
     if (s.d_dl) cudaFree(s.d_dl);
     if (s.d_dl_keys) cudaFree(s.d_dl_keys);
@@ -286,13 +290,11 @@ ESVO_API void esvo_destroy(esvo_ctx* c) {
     if (s.h_dl) cudaFreeHost(s.h_dl);
     if (s.stream && s.stream != c->s_main) cudaStreamDestroy(s.stream);
   }
-  for (auto& f : c->win) { cudaFree(f.pts); cudaFree(f.cnt); }
-  for (auto& f : c->win_pool) { cudaFree(f.pts); cudaFree(f.cnt); }
+  for (auto& f : c->win) { cudaFree(f.pts); cudaFree(f.cnt); if (f.last_read) cudaEventDestroy(f.last_read); }
+  for (auto& f : c->win_pool) { cudaFree(f.pts); cudaFree(f.cnt); if (f.last_read) cudaEventDestroy(f.last_read); }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
-  if (c->ev_fuse_done) cudaEventDestroy(c->ev_fuse_done);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->s_ts && c->s_ts != c->s_main) cudaStreamDestroy(c->s_ts);
-  if (c->s_fuse && c->s_fuse != c->s_main) cudaStreamDestroy(c->s_fuse);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
   if (c->s_main) cudaStreamDestroy(c->s_main);
   delete c;

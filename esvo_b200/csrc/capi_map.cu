@@ -12,13 +12,31 @@ int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius);
 
 template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
 
+// Window vectors are recycled through a FIFO pool.  A vector popped from the window may still be read by the
+// fusion of the frame that preceded the pop (running on another slot's stream), so it carries an event recorded
+// behind that fusion, and it is only reused after `depth` further frames: the wait below is then already satisfied.
 static int win_acquire(Ctx* c, size_t cap, Ctx::WinFrame& f) {
-  for (size_t i = 0; i < c->win_pool.size(); ++i)
-    if (c->win_pool[i].cap >= cap) { f = c->win_pool[i]; c->win_pool.erase(c->win_pool.begin() + i); return ESVO_OK; }
+  if (c->win_pool.size() > (size_t)c->depth)
+    for (size_t i = 0; i < c->win_pool.size() - (size_t)c->depth; ++i)
+      if (c->win_pool[i].cap >= cap) {
+        f = c->win_pool[i]; c->win_pool.erase(c->win_pool.begin() + i);
+        if (f.last_read) ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, f.last_read, 0));
+        return ESVO_OK;
+      }
   f = Ctx::WinFrame();
   f.cap = std::max<size_t>(cap, 1024);
   ESVO_CUDA_TRY(c, dmalloc(&f.pts, f.cap));
   ESVO_CUDA_TRY(c, dmalloc(&f.cnt, 1));
+  ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&f.last_read, cudaEventDisableTiming));
+  return ESVO_OK;
+}
+static int win_retire(Ctx* c, Ctx::WinFrame f) {
+  // last reader = the fusion of the previous frame (frame_no - 1), enqueued on that frame's slot stream
+  if (c->frame_no >= 1 && f.last_read) {
+    cudaStream_t st = c->slots[(int)((c->frame_no - 1) % (uint64_t)c->depth)].stream;
+    if (st) ESVO_CUDA_TRY(c, cudaEventRecord(f.last_read, st));
+  }
+  c->win_pool.push_back(f);
   return ESVO_OK;
 }
 
@@ -45,8 +63,6 @@ static int run_mapping_frame(Ctx* c) {
   c->prof_end(pe);
   ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_free, c->stream));               // the slot's observation buffers are free again
   sl.ev_free_valid = true;
-  // the window buffer we are about to overwrite may still be read by the previous frame's fusion
-  if (c->fuse_ever && c->s_fuse != c->stream) ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_fuse_done, 0));
   Ctx::WinFrame f;
   if ((rc = win_acquire(c, std::max<size_t>(c->n_ev, 1), f))) return rc;
   const double cost_thr = p.residual_vis_threshold * p.residual_vis_threshold * (double)(p.patch_size_x * p.patch_size_y);
@@ -71,15 +87,16 @@ static int run_mapping_frame(Ctx* c) {
     size_t tot;
     if ((rc = total(tot))) return rc;
     while ((double)tot > 1.5 * p.max_num_fusion_points && !c->win.empty()) {
-      c->win_pool.push_back(c->win.front()); c->win.erase(c->win.begin());
+      if ((rc = win_retire(c, c->win.front()))) return rc;
+      c->win.erase(c->win.begin());
       if ((rc = total(tot))) return rc;
     }
   } else {
-    while (c->win.size() > (size_t)p.max_num_fusion_frames) { c->win_pool.push_back(c->win.front()); c->win.erase(c->win.begin()); }
+    while (c->win.size() > (size_t)p.max_num_fusion_frames) {
+      if ((rc = win_retire(c, c->win.front()))) return rc;
+      c->win.erase(c->win.begin());
+    }
   }
-  ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_pts, c->stream));
-  StreamScope fuse_scope(c, c->s_fuse);                                   // the map is shared state: its own stream
-  ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->s_fuse, sl.ev_pts, 0));
   pe = c->prof_begin(5);
   if ((rc = fuse_reset_map(c, c->T_world_left))) return rc;               // :268-272 fresh DepthFrame at the obs pose
   if ((rc = fuse_zero_fusion_counter(c))) return rc;
@@ -101,14 +118,13 @@ static int run_mapping_frame(Ctx* c) {
   if (p.regularization && (rc = map_regularize(c))) return rc;            // :390-395
   rc = map_count(c);
   c->prof_end(pe);
-  ESVO_CUDA_TRY(c, cudaEventRecord(c->ev_fuse_done, c->s_fuse));
-  c->fuse_ever = true;
+  ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_fuse, c->stream));
+  sl.ev_fuse_valid = true;
   c->frame_no++;
   return rc;
 }
 
 static int fetch_mapping_counters(Ctx* c, uint64_t out[8]) {
-  if (c->s_fuse != c->stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_fuse));
   int rc = fetch_counters2(c);
   if (rc) return rc;
   unsigned long long sc[4];
@@ -177,13 +193,13 @@ ESVO_API int esvo_map_regularize(esvo_ctx* c) { CHECK_CTX(c); if (c->depth > 1) 
 ESVO_API int esvo_map_download(esvo_ctx* c, esvo_depth_point* out, size_t* n) {
   CHECK_CTX(c);
   if (!n) return ESVO_ERR_INVALID_ARG;
-  if (c->depth > 1 || c->s_fuse != c->stream) { int rc0 = drain(c); if (rc0) return rc0; }
+  if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }
   return map_download(c, out, n);
 }
 ESVO_API int esvo_mapping_reset(esvo_ctx* c) {
   CHECK_CTX(c);
   { int rc0 = drain(c); if (rc0) return rc0; }
-  for (auto& f : c->win) c->win_pool.push_back(f);
+  for (auto& f : c->win) c->win_pool.push_back(f);   // drained above: no reader is pending
   c->win.clear();
   return ESVO_OK;
 }
@@ -241,11 +257,11 @@ ESVO_API int esvo_results_begin(esvo_ctx* c, int64_t* ticket_out) {
   }
   if (!c->s_copy) ESVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
   {
-    StreamScope sc(c, c->s_fuse);   // right behind this frame's fusion, before the next frame resets the map
+    // right behind this frame's fusion on the slot's own stream
     int rc = map_gather_async(c, sl.d_dl, sl.d_dl_keys, sl.d_dlscal, sl.h_dlscal);
     if (rc) return rc;
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_counters, sl.d_counters, kCounters * 8, cudaMemcpyDeviceToHost, c->s_fuse));
-    ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_dl, c->s_fuse));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_counters, sl.d_counters, kCounters * 8, cudaMemcpyDeviceToHost, c->stream));
+    ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_dl, c->stream));
   }
   sl.dl_ticket = (int64_t)c->frame_no - 1;
   if (ticket_out) *ticket_out = sl.dl_ticket;
