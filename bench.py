@@ -110,7 +110,18 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner on stdout; the contract is ONE JSON line there
+        os.environ["NCCL_DEBUG"] = os.environ.get("NCCL_DEBUG", "WARN") if os.environ.get("NCCL_DEBUG", "").upper() not in ("VERSION", "") else "WARN"
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()      # forces communicator creation (and the banner) while stdout is redirected
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     prod = capi.load_product()
     l, r = configs.rig_calibs(RIG)
     prm = configs.params_for(RIG, prod)
