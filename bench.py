@@ -220,6 +220,8 @@ def run_ours(args, rank, world, local_rank):
         t_wall = time.perf_counter() - t_wall0
         launches = g.launch_count() - launches0
         step_ms = [e0.elapsed_time(e1)]
+        if os.environ.get("ESVO_BENCH_TIMELINE"):
+            g._call("profile_dump", [C.c_char_p], os.environ["ESVO_BENCH_TIMELINE"].encode())
         ms = (C.c_double * 8)(); cnt = (C.c_uint64 * 8)()
         g._call("profile_read", [f64, C.POINTER(C.c_uint64)], ms, cnt)
         g._call("profile", [C.c_int], 0)

@@ -117,7 +117,10 @@ int slot_alloc(Ctx* c, int i) {
 }
 int drain(Ctx* c) {
   if (c->s_ts) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_ts));
-  for (int i = 0; i < kMaxSlots; ++i) if (c->slots[i].stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->slots[i].stream));
+  for (int i = 0; i < kMaxSlots; ++i) {
+    if (c->slots[i].lm_stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->slots[i].lm_stream));
+    if (c->slots[i].stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->slots[i].stream));
+  }
   if (c->s_copy) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
   return ESVO_OK;
 }
@@ -288,6 +291,9 @@ ESVO_API void esvo_destroy(esvo_ctx* c) {
     if (s.d_dlscal) cudaFree(s.d_dlscal);
     if (s.h_dlscal) cudaFreeHost(s.h_dlscal);
     if (s.h_dl) cudaFreeHost(s.h_dl);
+    if (s.lm_stream) cudaStreamDestroy(s.lm_stream);
+    if (s.ev_seeds) cudaEventDestroy(s.ev_seeds);
+    if (s.ev_lm) cudaEventDestroy(s.ev_lm);
     if (s.stream && s.stream != c->s_main) cudaStreamDestroy(s.stream);
   }
   for (auto& f : c->win) { cudaFree(f.pts); cudaFree(f.cnt); if (f.last_read) cudaEventDestroy(f.last_read); }

@@ -58,7 +58,11 @@ static int run_mapping_frame(Ctx* c) {
   if ((rc = bm_run(c))) return rc;                                        // :308-309
   c->prof_end(pe); pe = c->prof_begin(2);
   if ((rc = seeds_order(c))) return rc;
-  c->prof_end(pe); pe = c->prof_begin(3);
+  c->prof_end(pe);
+  // (Measured: giving the LM kernel its own low-priority stream and the short stages high-priority streams made
+  //  the pipeline slower and erratic on B200 -- 0.97-1.4 ms/frame instead of 0.85 -- so everything of a frame
+  //  stays on the slot's single stream.)
+  pe = c->prof_begin(3);
   if ((rc = lm_run(c, c->d_seeds, 0))) return rc;                         // :330
   c->prof_end(pe);
   ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_free, c->stream));               // the slot's observation buffers are free again
@@ -97,6 +101,12 @@ static int run_mapping_frame(Ctx* c) {
       c->win.erase(c->win.begin());
     }
   }
+  ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_pts, c->stream));
+  sl.ev_pts_valid = true;
+  // the window holds vectors written by the point-ordering kernels of the previous frames, which run on
+  // other slots' streams and may finish later than ours (LM tails): wait for them (not for their fusions)
+  for (int i = 0; i < c->depth; ++i)
+    if (i != c->cur && c->slots[i].ev_pts_valid) ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->slots[i].ev_pts, 0));
   pe = c->prof_begin(5);
   if ((rc = fuse_reset_map(c, c->T_world_left))) return rc;               // :268-272 fresh DepthFrame at the obs pose
   if ((rc = fuse_zero_fusion_counter(c))) return rc;
@@ -303,6 +313,27 @@ ESVO_API int esvo_results_end(esvo_ctx* c, int64_t ticket, esvo_depth_point* out
 }
 ESVO_API uint64_t esvo_debug_counter(esvo_ctx* c, int idx) { return (c && idx >= 0 && idx < kCounters) ? c->h_counters[idx] : 0; }
 ESVO_API int esvo_profile(esvo_ctx* c, int enable) { CHECK_CTX(c); c->prof = enable != 0; return ESVO_OK; }
+// Debug: dump every recorded (stage, begin, end) as a timeline in ms relative to the earliest event.
+ESVO_API int esvo_profile_dump(esvo_ctx* c, const char* path) {
+  CHECK_CTX(c);
+  int rc0 = drain(c);
+  if (rc0) return rc0;
+  cudaEvent_t ref = nullptr;
+  for (int s = 0; s < 8 && !ref; ++s) if (!c->prof_ev[s].empty()) ref = c->prof_ev[s][0].first;
+  if (!ref) return ESVO_ERR_STATE;
+  FILE* f = fopen(path, "w");
+  if (!f) return ESVO_ERR_INVALID_ARG;
+  fprintf(f, "stage,index,begin_ms,end_ms\n");
+  for (int s = 0; s < 8; ++s)
+    for (size_t i = 0; i < c->prof_ev[s].size(); ++i) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, ref, c->prof_ev[s][i].first);
+      cudaEventElapsedTime(&b, ref, c->prof_ev[s][i].second);
+      fprintf(f, "%d,%zu,%.4f,%.4f\n", s, i, a, b);
+    }
+  fclose(f);
+  return ESVO_OK;
+}
 ESVO_API int esvo_profile_read(esvo_ctx* c, double ms[8], uint64_t cnt[8]) {
   CHECK_CTX(c);
   ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));

@@ -264,7 +264,7 @@ ESVO_API int esvo_stage_mapping_inputs(esvo_ctx* ctx, const uint16_t* ex, const 
 ESVO_API int esvo_run_mapping(esvo_ctx* ctx);
 ESVO_API int esvo_fetch_mapping_counters(esvo_ctx* ctx, uint64_t counters_out[8]);
 ESVO_API int esvo_sync(esvo_ctx* ctx);
-/* Software pipelining of consecutive mapping frames (1 = strictly sequential, the default; up to 8).
+/* Software pipelining of consecutive mapping frames (1 = strictly sequential, the default; up to 16).
  * With depth S the frames issued through esvo_set_ts_pair_dev / esvo_stage_mapping_inputs(_dev) /
  * esvo_run_mapping rotate over S buffer sets and CUDA streams so that the serial tail of one frame's
  * LM kernel overlaps with the next frames; results are identical to depth 1. */
