@@ -40,6 +40,24 @@ RIGS = {
             D=[-0.0949368, 0.202115, 0.000582129, 0.00145529],
             R=[0.999963, 0.00818053, -0.00267849, -0.0081745, 0.999964, 0.00225394, 0.00269683, -0.00223196, 0.999994],
             P=[534.094, 0, 335.446, -319.94, 0, 534.094, 223.233, 0, 0, 0, 1, 0])),
+    # calib/upenn/{left,right}.yaml -- the reference's equidistant (fisheye) rig
+    "upenn": dict(
+        width=346, height=260, model="equidistant",
+        left=dict(
+            K=[226.38018519795807, 0.0, 173.6470807871759, 0.0, 226.15002947047415, 133.73271487507847, 0, 0, 1],
+            D=[-0.048031442223833355, 0.011330957517194437, -0.055378166304281135, 0.021500973881459395],
+            R=[0.999877311526236, 0.015019439766575743, -0.004447282784398257,
+               -0.014996983873604017, 0.9998748347535599, 0.005040367172759556,
+               0.004522429630305261, -0.004973052949604937, 0.9999774079320989],
+            P=[199.6530123165822, 0.0, 177.43276376280926, 0.0, 0.0, 199.6530123165822, 126.81215684365904, 0.0, 0.0, 0.0, 1.0, 0.0]),
+        right=dict(
+            K=[226.0181418548734, 0, 174.5433576736815, 0, 225.7869434267677, 124.21627572590607, 0, 0, 1],
+            D=[-0.04846669832871334, 0.010092844338123635, -0.04293073765014637, 0.005194706897326005],
+            R=[0.9999922706537476, 0.003931701344419404, -1.890238450965101e-05,
+               -0.003931746704476347, 0.9999797362744968, -0.005006836150689904,
+               -7.83382948021244e-07, 0.0050068717705076754, 0.9999874655386736],
+            P=[199.6530123165822, 0.0, 177.43276376280926, -19.941771812941038, 0.0, 199.6530123165822, 126.81215684365904, 0.0,
+               0.0, 0.0, 1.0, 0.0])),
 }
 
 
@@ -94,6 +112,14 @@ def params_for(name, lib) -> capi.Params:
         p.reg_radius, p.reg_min_neighbours, p.reg_min_close_neighbours = 20, 32, 32
         p.td_nu, p.td_scale = 2.182, 17.277
         p.bm_min_disparity, p.bm_max_disparity = 0, 150
+        p.trk_batch_size = 300
+    elif name == "upenn":   # cfg/mapping/mapping_upenn.yaml, cfg/tracking/tracking_upenn.yaml
+        p.invdepth_min_range, p.invdepth_max_range = 0.16, 1.0
+        p.residual_vis_threshold = 20; p.stdvar_vis_threshold = 0.15
+        p.fusion_radius = 0; p.max_num_fusion_frames = 40; p.max_num_fusion_points = 3000
+        p.smooth_time_surface = 0; p.regularization = 0
+        p.td_nu, p.td_scale = 2.182, 17.277
+        p.bm_min_disparity, p.bm_max_disparity = 1, 40
         p.trk_batch_size = 300
     else:
         raise KeyError(name)

@@ -8,7 +8,9 @@
 // ROS / Eigen / OpenCV types are replaced by plain structs: ros::Time -> int64 ns, Transformation -> row-major
 // double[16], cv::Mat mono8 -> uint8_t*, dvs_msgs::Event -> esvo::Event.  Header-only; link with libesvo_b200.so.
 #pragma once
+#include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
@@ -233,6 +235,48 @@ class RegProblemSolverLM {
 };
 
 }  // namespace core
+
+// The event front-end of esvo_Mapping::dataTransferring (esvo_Mapping.cpp:536-603), host logic feeding the hot path:
+//  * selectCloseEvents: the newest-first, at most PROCESS_EVENT_NUM left events with stamps in
+//    [t_end - 10*BM_half_slice_thickness, t_end)  (:562-575; events_left_ is time-ordered);
+//  * samplePoseStamps: the virtual-view stamps t_begin, t_begin + 0.05*BM_half_slice_thickness, ... <= t_end at
+//    which the node looks up tf poses to fill st_map_ (:585-599).
+// Both use the reference's ros::Time <-> double conversions (toSec() compares, Time(double) construction).
+namespace frontend {
+inline double toSec(int64_t ns) { int64_t s = ns / 1000000000LL, n = ns % 1000000000LL; if (n < 0) { n += 1000000000LL; --s; } return (double)s + 1e-9 * (double)n; }
+inline int64_t fromSec(double t) {   // ros::Time(double): sec = floor(t), nsec = round((t - sec) * 1e9), carry on overflow
+  int64_t sec = (int64_t)std::floor(t);
+  int64_t nsec = (int64_t)std::llround((t - (double)sec) * 1e9);
+  sec += nsec / 1000000000LL; nsec %= 1000000000LL;
+  return sec * 1000000000LL + nsec;
+}
+inline void selectCloseEvents(std::vector<esvo::Event>& events_left /* time-ordered */, int64_t t_end_ns, double BM_half_slice_thickness,
+                              size_t PROCESS_EVENT_NUM, std::vector<esvo::Event*>& vCloseEventsPtr_left) {
+  vCloseEventsPtr_left.clear();
+  if (events_left.empty()) return;
+  const double t_end = toSec(t_end_ns);
+  const int64_t t_begin_ns = fromSec(std::max(0.0, t_end - 10 * BM_half_slice_thickness));
+  auto lower = [&](int64_t t) {   // tools::EventBuffer_lower_bound (utils.h:50-55): ros::Time (integer) comparison
+    size_t lo = 0, hi = events_left.size();
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (events_left[mid].ts < t) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  size_t ev_end = lower(t_end_ns);
+  const size_t ev_begin = lower(t_begin_ns);
+  if (ev_end == events_left.size()) return;   // the reference dereferences end() here (UB); no event at/after t_end -> nothing to add
+  while (ev_end != ev_begin && vCloseEventsPtr_left.size() < PROCESS_EVENT_NUM) {
+    vCloseEventsPtr_left.push_back(&events_left[ev_end]);   // note: starts AT lower_bound(t_end), like the reference (:570-574)
+    --ev_end;
+  }
+}
+inline std::vector<int64_t> samplePoseStamps(int64_t t_end_ns, double BM_half_slice_thickness) {
+  std::vector<int64_t> out;
+  const double t_end = toSec(t_end_ns);
+  int64_t t_tmp = fromSec(std::max(0.0, t_end - 10 * BM_half_slice_thickness));
+  while (toSec(t_tmp) <= t_end) { out.push_back(t_tmp); t_tmp = fromSec(toSec(t_tmp) + 0.05 * BM_half_slice_thickness); }
+  return out;
+}
+}  // namespace frontend
 
 // esvo_core::esvo_Mapping::MappingAtTime (esvo_Mapping.cpp:261-399) as one call with device-resident hand-off.
 class esvo_Mapping {

@@ -31,3 +31,11 @@ def test_cpp_shim_runs_on_gpu(product_lib):
     p = subprocess.run([EXE], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "BM 500 seeds" in p.stdout, p.stdout
+
+
+def test_cpp_shim_event_frontend_helpers(tmp_path):
+    """esvo_core::frontend (selectCloseEvents / samplePoseStamps, esvo_Mapping.cpp:536-603) -- host logic, header-only."""
+    exe = str(tmp_path / "frontend_check")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "frontend_check.cpp"), "-o", exe])
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr

@@ -4,7 +4,7 @@ in practice ~1e-9."""
 import numpy as np
 import pytest
 
-from esvo_b200 import capi
+from esvo_b200 import capi, configs, synth
 from util import build_ts_pair, make_backends, rel, scenario
 
 pytestmark = pytest.mark.gpu
@@ -307,3 +307,39 @@ def test_time_surface_log_eviction(oracle_lib, product_lib):
         io, to = o.ts_build(0, T); ig, tg = g.ts_build(0, T)
         assert np.array_equal(io, ig), f"T={T}: {(io != ig).sum()} idx mismatches"
         assert np.array_equal(to, tg)
+
+
+@pytest.mark.parametrize("rig", ["hkust", "dsec", "upenn"])
+def test_product_rectification_tables_match_oracle(oracle_lib, product_lib, rig):
+    """The library's own one-time host setup (maps, raw->rectified LUT, validity mask, baseline, disparity clip)
+    against the oracle's, for plumb_bob and equidistant rigs."""
+    l, r = configs.rig_calibs(rig)
+    o = capi.Backend(oracle_lib, l, r, configs.params_for(rig, oracle_lib))
+    g = capi.Backend(product_lib, l, r, configs.params_for(rig, product_lib))
+    assert o.get_derived() == pytest.approx(g.get_derived(), rel=1e-14)
+    for cam in (0, 1):
+        to, tg = o.get_rectify_tables(cam), g.get_rectify_tables(cam)
+        assert np.abs(to[0] - tg[0]).max() < 1e-4 and np.abs(to[1] - tg[1]).max() < 1e-4
+        assert np.abs(to[2] - tg[2]).max() < 1e-4
+        assert (to[3] != tg[3]).mean() < 1e-4
+
+
+def test_equidistant_rig_frame_parity(oracle_lib, product_lib):
+    """One mapping frame on the reference's equidistant (upenn) rig, each side using ITS OWN rectification tables."""
+    s = synth.make_stream("hkust", seed=6, n_seeds=800)      # event geometry from the hkust generator is fine: same sensor size
+    l, r = configs.rig_calibs("upenn")
+    o = capi.Backend(oracle_lib, l, r, configs.params_for("upenn", oracle_lib))
+    g = capi.Backend(product_lib, l, r, configs.params_for("upenn", product_lib))
+    for cam in (0, 1):
+        g.set_rectify_tables(cam, *o.get_rectify_tables(cam))
+    res = []
+    for be in (o, g):
+        tl, tr = build_ts_pair(be, s)
+        be.set_ts_pair(tl, tr, s["T_world_left"])
+        sd = s["seeds"]
+        c = be.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+        res.append((tl, tr, c, be.map_download()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    for key in ("n_seeds", "n_solved", "n_culled", "bm_evals", "n_fusions", "map_size"):
+        assert res[0][2][key] == res[1][2][key], (key, res[0][2], res[1][2])
+    assert np.array_equal(res[0][3]["row"], res[1][3]["row"])

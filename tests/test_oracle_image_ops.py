@@ -89,3 +89,24 @@ def test_rectification_tables_match_cv2(oracle_lib, rig):
         mk = (cv2.remap(ones, r1, r2, cv2.INTER_LINEAR) > 0.999).astype(np.uint8) * 255
         # the mask is computed from the maps; allow the handful of pixels whose map differs by an ulp
         assert (mask != mk).mean() < 1e-3
+
+
+def test_equidistant_rectification_tables_match_cv2_fisheye(oracle_lib):
+    """calib/upenn is the reference's equidistant rig: cv::fisheye::initUndistortRectifyMap / undistortPoints
+    (TimeSurface.cpp:341-346,380-385, CameraSystem.cpp:76-92)."""
+    l, r = configs.rig_calibs("upenn")
+    b = capi.Backend(oracle_lib, l, r, configs.params_for("upenn", oracle_lib))
+    arr = configs.rig_arrays("upenn")
+    W, H = arr["width"], arr["height"]
+    for cam, side in ((0, "left"), (1, "right")):
+        c = arr[side]
+        m1, m2, lut, mask = b.get_rectify_tables(cam)
+        r1, r2 = cv2.fisheye.initUndistortRectifyMap(c["K"], c["D"].reshape(4, 1), c["R"], c["P"], (W, H), cv2.CV_32FC1)
+        assert np.abs(m1 - r1).max() < 2e-3 and np.abs(m2 - r2).max() < 2e-3
+        raw = np.stack(np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32)), -1).reshape(-1, 1, 2)
+        und = cv2.fisheye.undistortPoints(raw, c["K"], c["D"].reshape(4, 1), R=c["R"], P=c["P"]).reshape(H, W, 2)
+        assert np.abs(lut - und).max() < 2e-3
+        ones = np.ones((H, W), np.float32)
+        mk = (cv2.remap(ones, r1, r2, cv2.INTER_LINEAR) > 0.1).astype(np.uint8) * 255
+        assert (mask != mk).mean() < 1e-3
+    assert abs(b.get_derived()["baseline"] - 19.941771812941038 / 199.6530123165822) < 1e-12
