@@ -50,22 +50,63 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed regions.
+
+    In-process NVML (nvidia_ml_py) by default: a query is a ~20 us ioctl.  The `nvidia-smi -lms` loop it replaces
+    (still available: ESVO_BENCH_SAMPLER=smi) re-enumerates the device state on every tick under the driver lock,
+    which stalled kernel submission for milliseconds at a time and made the pipelined timing bimodal."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.rows, self._stop_evt, self.proc = gpu, [], threading.Event(), None
+        self.period = float(os.environ.get("ESVO_BENCH_SMI_MS", "25")) / 1e3
+        self.windows, self.stamps = [], []     # timed regions (perf_counter pairs); sample time stamps
+        self.mode = os.environ.get("ESVO_BENCH_SAMPLER", "nvml")
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it lists indices
+        idx = self.gpu
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")) and self.gpu < len(vis.split(",")):
+            idx = int(vis.split(",")[self.gpu])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        while not self._stop_evt.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append([str(sm), str(mx)] + ["Active" if mask & bit else "Not Active" for bit, _ in self.REASONS])
+            self.stamps.append(time.perf_counter())
+            self._stop_evt.wait(self.period)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-lms", str(max(1, int(self.period * 1e3)))], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+            self.stamps.append(time.perf_counter())
+            if self._stop_evt.is_set():
+                break
+
+    def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", os.environ.get("ESVO_BENCH_SMI_MS", "100")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-                if self._stop_evt.is_set():
-                    break
+            if self.mode == "nvml":
+                try:
+                    self._run_nvml()
+                    return
+                except Exception:
+                    if self.rows:
+                        return
+                    self.mode = "smi"
+            self._run_smi()
         except Exception:
             pass
 
@@ -73,15 +114,20 @@ class ClockSampler(threading.Thread):
         self._stop_evt.set()
         if self.proc:
             self.proc.terminate()
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = self.rows
+        if self.windows:     # keep the samples taken inside the timed regions (all of them if none fell inside)
+            inside = [r for r, t in zip(self.rows, self.stamps) if any(a <= t <= b for a, b in self.windows)]
+            rows = inside or rows
+        sm = [int(r[0]) for r in rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+        for r in rows:
+            for (_, name), v in zip(self.REASONS, r[2:6]):
                 if v == "Active":
                     reasons.add(name)
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampler": self.mode,
+                "scope": "samples inside the two timed regions" if rows is not self.rows else "whole run"}
 
 
 def make_workload(seed):
@@ -137,8 +183,9 @@ def run_ours(args, rank, world, local_rank):
     base = make_workload(seed=_ed.stream_seed(rank))
     K, Wm = args.steps, args.warmup
     NP = prm.max_num_fusion_frames
-    allf = [shifted(base, k) for k in range(NP + 2 * (K + Wm) + 2)]
-    frames_prime, frames = allf[:NP], allf[NP:]
+    KP = min(K, 48)                         # steps of the separately profiled pass (per-stage breakdown)
+    allf = [shifted(base, k) for k in range(NP + KP + 2 * (K + Wm) + 2)]
+    frames_prime, frames_prof, frames = allf[:NP], allf[NP:NP + KP], allf[NP + KP:]
     stream = torch.cuda.ExternalStream(g.stream(), device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -152,6 +199,7 @@ def run_ours(args, rank, world, local_rank):
         d["pose_t"] = dev(f["pose_t"]); d["poses"] = dev(f["poses"])
         return d
     dframes_prime = [to_dev(f) for f in frames_prime]
+    dframes_prof = [to_dev(f) for f in frames_prof]
     dframes = [to_dev(f) for f in frames[: K + Wm]]
     torch.cuda.synchronize()
     u16, i64, u8, f64 = C.POINTER(C.c_uint16), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_double)
@@ -183,17 +231,26 @@ def run_ours(args, rank, world, local_rank):
         # prime the 20-frame fusion window (stream state, like a tracker that has been running), then W warm-up steps
         for k in range(prm.max_num_fusion_frames):
             step_resident(frames_prime[k], dframes_prime[k])
+        # per-stage breakdown: a separately profiled pass (every stage bracketed with CUDA events), NOT part of `value`
+        g.sync()
+        g._call("profile", [C.c_int], 0xFF)
+        g._call("profile_read", [f64, C.POINTER(C.c_uint64)], (C.c_double * 8)(), (C.c_uint64 * 8)())
+        for k in range(KP):
+            step_resident(frames_prof[k], dframes_prof[k])
+        g.sync()
+        if os.environ.get("ESVO_BENCH_TIMELINE"):
+            g._call("profile_dump", [C.c_char_p], os.environ["ESVO_BENCH_TIMELINE"].encode())
+        ms = (C.c_double * 8)(); cnt = (C.c_uint64 * 8)()
+        g._call("profile_read", [f64, C.POINTER(C.c_uint64)], ms, cnt)
+        g._call("profile", [C.c_int], 0)
         for k in range(Wm):
             step_resident(frames[k], dframes[k])
         g.sync()
         ctr = g.fetch_mapping_counters()
-        g._call("profile", [C.c_int], 1)
+        # inside the timed region only the dominant kernel's stage (3 = depth LM) is bracketed with CUDA events (two
+        # records per step on its own stream); the full per-stage breakdown comes from the separate profiled pass above
+        g._call("profile", [C.c_int], 1 << 3)
         g._call("profile_read", [f64, C.POINTER(C.c_uint64)], (C.c_double * 8)(), (C.c_uint64 * 8)())
-        sampler = ClockSampler(local_rank); sampler.start()
-    t_wait = time.time()
-    while not sampler.rows and time.time() - t_wait < 15:     # nvidia-smi start-up is over once the first row arrives
-        time.sleep(0.05)
-        time.sleep(0.3)
         g.sync()
         flush.fill_(7)            # evict everything (inputs of the timed steps included) from L2 before the timed region
         barrier()
@@ -202,30 +259,32 @@ def run_ours(args, rank, world, local_rank):
         t_wall0 = time.perf_counter()
         e0.record(stream)
         host_prof = {}
-        if os.environ.get("ESVO_BENCH_HOSTPROF") == "1":
+        hostprof_on = os.environ.get("ESVO_BENCH_HOSTPROF") == "1"
+        if hostprof_on:
             orig_call = g._call
             def timed_call(name, *a, **kw):
                 t = time.perf_counter(); r = orig_call(name, *a, **kw); host_prof[name] = host_prof.get(name, 0.0) + time.perf_counter() - t
                 return r
             g._call = timed_call
+        issue_t = [time.perf_counter()]
         for k in range(Wm, Wm + K):
             step_resident(frames[k], dframes[k])
+            issue_t.append(time.perf_counter())
         host_prof["issue_total"] = time.perf_counter() - t_wall0
-        if os.environ.get("ESVO_BENCH_HOSTPROF") == "1":
-            g._call = orig_call
-            print({k: round(v * 1e3 / K, 4) for k, v in host_prof.items()}, file=sys.stderr)
+        if hostprof_on:
+            print("resident", {k: round(v * 1e3 / K, 4) for k, v in host_prof.items()}, file=sys.stderr)
+            host_prof.clear()
         g.sync()                                       # every stream of the library drained
         e1.record(stream)
         barrier()
         t_wall = time.perf_counter() - t_wall0
+        sampler.windows.append((t_wall0, t_wall0 + t_wall))
         launches = g.launch_count() - launches0
         step_ms = [e0.elapsed_time(e1)]
-        if os.environ.get("ESVO_BENCH_TIMELINE"):
-            g._call("profile_dump", [C.c_char_p], os.environ["ESVO_BENCH_TIMELINE"].encode())
-        ms = (C.c_double * 8)(); cnt = (C.c_uint64 * 8)()
-        g._call("profile_read", [f64, C.POINTER(C.c_uint64)], ms, cnt)
-        g._call("profile", [C.c_int], 0)
+        ms_lm = (C.c_double * 8)(); cnt_lm = (C.c_uint64 * 8)()
+        g._call("profile_read", [f64, C.POINTER(C.c_uint64)], ms_lm, cnt_lm)
         ctr = g.fetch_mapping_counters()
+        g._call("profile", [C.c_int], 0)
     total_ms = float(np.sum(step_ms))
     evals_ref_equiv = ctr["bm_evals"] + ctr["lm_evals"]
     # executed LM evaluations (the kernel re-uses f(x) inside the forward difference instead of recomputing it)
@@ -281,17 +340,24 @@ def run_ours(args, rank, world, local_rank):
         step_e2e(f)
     drain_e2e()
     h2d = d2h = 0
+    host_prof.clear()
     barrier()
     t0 = time.perf_counter()
+    issue_e = [time.perf_counter()]
     for f in pinned[Wm: Wm + K]:
         step_e2e(f)
+        issue_e.append(time.perf_counter())
+    if hostprof_on:
+        print("e2e", {k: round(v * 1e3 / K, 4) for k, v in host_prof.items()}, "issue_total", round((issue_e[-1] - issue_e[0]) * 1e3 / K, 4), file=sys.stderr)
+        g._call = orig_call
     ce = drain_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    sampler.windows.append((t0, t0 + e2e_s))
     clocks = sampler.stop()
     e2e_evals = ce["bm_evals"] + ce["lm_evals"]
     # TS-only rate (second half of the metric): resident events -> rectified u8 TS, both cameras per step
-    ts_frames_per_s = 2 * K / (ms[0] / 1e3) if ms[0] > 0 else None
+    ts_frames_per_s = 2 * KP / (ms[0] / 1e3) if ms[0] > 0 else None
 
     # timing = max over ranks, work = sum over ranks, one result record per stream (esvo_b200/dist.py)
     from esvo_b200 import dist as edist
@@ -305,7 +371,7 @@ def run_ours(args, rank, world, local_rank):
     value = evals_all * K / (total_ms / 1e3)
     e2e_value = e2e_evals_all * K / (e2e_ms / 1e3)
     # roofline of the dominant kernel of the step
-    bm_ms, lm_ms = ms[1] / max(cnt[1], 1), ms[3] / max(cnt[3], 1)
+    bm_ms, lm_ms = ms[1] / max(cnt[1], 1), ms_lm[3] / max(cnt_lm[3], 1)   # LM: live, inside the timed region
     ncand = ctr["bm_evals"] / max(ctr["n_events"], 1)
     bm_bytes = ctr["bm_evals"] * BM_BYTES * (1 + 1 / max(ncand, 1))
     lm_bytes = lm_exec * LM_BYTES
@@ -339,12 +405,17 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": dom, "roofline_other": other,
         "ts_frames_per_s": ts_frames_per_s,
-        "breakdown_ms_per_step": {"time_surface_x2": ms[0] / K, "block_matching": ms[1] / K, "seed_order": ms[2] / K,
-                                  "depth_lm": ms[3] / K, "point_order_cull": ms[4] / K, "fusion_clean_regularise": ms[5] / K},
+        # stage durations with frames of other pipeline slots running concurrently (they overlap: the sum exceeds ms_per_step)
+        "breakdown_ms_per_step": {"time_surface_x2": ms[0] / KP, "block_matching": ms[1] / KP, "seed_order": ms[2] / KP,
+                                  "depth_lm": ms[3] / KP, "point_order_cull": ms[4] / KP, "fusion_clean_regularise": ms[5] / KP,
+                                  "source": f"separate profiled pass of {KP} steps before the warm-up"},
         "per_step": {"bm_evals": ctr["bm_evals"], "lm_evals_reference_equivalent": ctr["lm_evals"], "lm_evals_executed": lm_exec,
                      "n_seeds": ctr["n_seeds"], "n_solved": ctr["n_solved"], "n_culled": ctr["n_culled"],
                      "n_fusions": ctr["n_fusions"], "map_size": ctr["map_size"]},
         "wall_s_timed_region": t_wall,
+        # host-side time per step() call (enqueue only; large values = the submission queue was full or the host stalled)
+        "host_issue_ms": {leg: {"mean": float(np.mean(np.diff(t)) * 1e3), "p99": float(np.percentile(np.diff(t), 99) * 1e3),
+                                "max": float(np.max(np.diff(t)) * 1e3)} for leg, t in (("resident", issue_t), ("e2e", issue_e))},
         "streams": [dict(zip(edist.RECORD_FIELDS, [float(v) for v in r])) for r in records],
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -312,7 +312,13 @@ ESVO_API int esvo_results_end(esvo_ctx* c, int64_t ticket, esvo_depth_point* out
   return ESVO_OK;
 }
 ESVO_API uint64_t esvo_debug_counter(esvo_ctx* c, int idx) { return (c && idx >= 0 && idx < kCounters) ? c->h_counters[idx] : 0; }
-ESVO_API int esvo_profile(esvo_ctx* c, int enable) { CHECK_CTX(c); c->prof = enable != 0; return ESVO_OK; }
+ESVO_API int esvo_profile(esvo_ctx* c, int stage_mask) {
+  CHECK_CTX(c);
+  c->prof = (unsigned)stage_mask & 0xffu;
+  // Events are created here, not on the hot path: enough for ~512 records before the next esvo_profile_read.
+  if (c->prof) while (c->prof_pool.size() < 1024) { cudaEvent_t e; ESVO_CUDA_TRY(c, cudaEventCreate(&e)); c->prof_pool.push_back(e); }
+  return ESVO_OK;
+}
 // Debug: dump every recorded (stage, begin, end) as a timeline in ms relative to the earliest event.
 ESVO_API int esvo_profile_dump(esvo_ctx* c, const char* path) {
   CHECK_CTX(c);

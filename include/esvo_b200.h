@@ -289,13 +289,14 @@ ESVO_API int esvo_stage_mapping_inputs_dev(esvo_ctx* ctx, const uint16_t* ex_dev
 ESVO_API int esvo_set_ts_pair_dev(esvo_ctx* ctx, const double T_world_left[16]);
 /* Per-stage device timing with CUDA events on the ctx stream.  Stages: 0 time surface, 1 block
  * matching, 2 seed ordering, 3 depth LM, 4 point ordering/culling, 5 fusion+clean+regularise,
- * 6 tracking.  esvo_profile_read synchronises, returns accumulated ms and launch counts per stage
- * since the last read and clears them. */
+ * 6 tracking.  esvo_profile(ctx, stage_mask): bit s switches the timing of stage s on (0 = off, 0xff = all).
+ * esvo_profile_read synchronises, returns accumulated ms and launch counts per stage since the last read
+ * and clears them. */
 /* Raw device counters of the last esvo_fetch_mapping_counters / esvo_mapping_at_time
  * (idx 7 = DepthProblem evaluations actually executed by the LM kernel, which re-uses f(x) inside
  * the forward difference instead of recomputing it like NumericalDiff does). */
 ESVO_API uint64_t esvo_debug_counter(esvo_ctx* ctx, int idx);
-ESVO_API int esvo_profile(esvo_ctx* ctx, int enable);
+ESVO_API int esvo_profile(esvo_ctx* ctx, int stage_mask);
 ESVO_API int esvo_profile_read(esvo_ctx* ctx, double ms_out[8], uint64_t count_out[8]);
 /* CUDA stream of the ctx (cudaStream_t as void*), so callers can record events on it. */
 ESVO_API void* esvo_stream(esvo_ctx* ctx);
