@@ -157,9 +157,13 @@ class Backend:
         self.ctx = C.c_void_p(self.ctx)
 
     def _call(self, name, argtypes, *args, ok=(0,)):
-        f = self.L.fn(name)
-        f.argtypes = [C.c_void_p] + list(argtypes)
-        f.restype = C.c_int
+        cache = self.__dict__.setdefault("_fn_cache", {})
+        f = cache.get(name)
+        if f is None:                      # prototypes are set once per entry point (this sits on the per-frame path)
+            f = self.L.fn(name)
+            f.argtypes = [C.c_void_p] + list(argtypes)
+            f.restype = C.c_int
+            cache[name] = f
         rc = f(self.ctx, *args)
         if rc not in ok:
             msg = ""

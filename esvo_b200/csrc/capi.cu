@@ -116,7 +116,7 @@ int slot_alloc(Ctx* c, int i) {
   return ESVO_OK;
 }
 int drain(Ctx* c) {
-  if (c->s_ts) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_ts));
+  for (int k = 0; k < 2; ++k) if (c->s_tsc[k]) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_tsc[k]));
   for (int i = 0; i < kMaxSlots; ++i) {
     if (c->slots[i].lm_stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->slots[i].lm_stream));
     if (c->slots[i].stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->slots[i].stream));
@@ -199,10 +199,18 @@ ESVO_API int esvo_set_pipeline_depth(esvo_ctx* c, int depth) {
   if (rc) return rc;
   slot_save(c);
   if (depth > 1) {
-    if (c->s_ts == c->s_main) ESVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_ts, cudaStreamNonBlocking));
+    // The time-surface chain of a frame is ~8 short dependent kernels per camera; with the SMs saturated by the
+    // LM kernels of the frames in flight, each of them would queue behind pending LM blocks.  The two cameras get
+    // their own streams, at the highest priority: their blocks are placed as soon as any LM block retires.
+    static const bool prio = [] { const char* e = getenv("ESVO_TS_PRIO"); return e ? atoi(e) != 0 : true; }();
+    int lo = 0, hi = 0;
+    ESVO_CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int k = 0; k < 2; ++k)
+      if (c->s_tsc[k] == c->s_main) ESVO_CUDA_TRY(c, cudaStreamCreateWithPriority(&c->s_tsc[k], cudaStreamNonBlocking, prio ? hi : lo));
+    if (!c->ev_ts_join) ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ts_join, cudaEventDisableTiming));
     for (int i = 1; i < depth; ++i) if ((rc = slot_alloc(c, i))) return rc;
   } else {
-    if (c->s_ts != c->s_main) { cudaStreamDestroy(c->s_ts); c->s_ts = c->s_main; }
+    for (int k = 0; k < 2; ++k) if (c->s_tsc[k] != c->s_main) { cudaStreamDestroy(c->s_tsc[k]); c->s_tsc[k] = c->s_main; }
   }
   c->depth = depth;
   c->frame_no = 0;
@@ -248,7 +256,7 @@ ESVO_API esvo_ctx* esvo_create(int device, const esvo_calib* left, const esvo_ca
   if (d.dmax >= d.dmin && (d.dmax - d.dmin) / d.step + 1 > 192 && d.step > 1) { delete c; return fail(ESVO_ERR_UNSUPPORTED); }
   auto bail = [&](int code) -> esvo_ctx* { esvo_destroy(c); return fail(code); };
   if (cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) != cudaSuccess) return bail(ESVO_ERR_CUDA);
-  c->stream = c->s_ts = c->s_main;
+  c->stream = c->s_tsc[0] = c->s_tsc[1] = c->s_main;
   c->slots[0].stream = c->s_main;
   const size_t npix = (size_t)d.W * d.H;
   if (slot_alloc(c, 0)) return bail(ESVO_ERR_CUDA);
@@ -300,7 +308,8 @@ ESVO_API void esvo_destroy(esvo_ctx* c) {
   for (auto& f : c->win_pool) { cudaFree(f.pts); cudaFree(f.cnt); if (f.last_read) cudaEventDestroy(f.last_read); }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
   if (c->h_stage) cudaFreeHost(c->h_stage);
-  if (c->s_ts && c->s_ts != c->s_main) cudaStreamDestroy(c->s_ts);
+  for (int k = 0; k < 2; ++k) if (c->s_tsc[k] && c->s_tsc[k] != c->s_main) cudaStreamDestroy(c->s_tsc[k]);
+  if (c->ev_ts_join) cudaEventDestroy(c->ev_ts_join);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
   if (c->s_main) cudaStreamDestroy(c->s_main);
   delete c;
@@ -314,6 +323,7 @@ ESVO_API int esvo_set_rectify_tables(esvo_ctx* c, int cam, const float* m1, cons
   if (m1) c->cam[cam].map1.assign(m1, m1 + n);
   if (m2) c->cam[cam].map2.assign(m2, m2 + n);
   if (lut) c->cam[cam].lut.assign(lut, lut + 2 * n);
+  c->tables_version++;
   if (mask) c->cam[cam].mask.assign(mask, mask + n);
   ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return upload_tables(c);
@@ -339,14 +349,14 @@ ESVO_API int esvo_stage_ts_events(esvo_ctx* c, int cam, const uint16_t* x, const
                                   const uint8_t* pol, size_t n) {
   CHECK_CTX(c);
   if (cam < 0 || cam > 1 || (n && (!x || !y || !t))) return ESVO_ERR_INVALID_ARG;
-  StreamScope sc(c, c->s_ts);
+  StreamScope sc(c, c->s_tsc[cam]);
   return ts_push(c, cam, x, y, t, pol, n, false);
 }
 ESVO_API int esvo_ts_push_events_dev(esvo_ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t,
                                      const uint8_t* pol, size_t n) {
   CHECK_CTX(c);
   if (cam < 0 || cam > 1 || (n && (!x || !y || !t))) return ESVO_ERR_INVALID_ARG;
-  StreamScope sc(c, c->s_ts);
+  StreamScope sc(c, c->s_tsc[cam]);
   return ts_push(c, cam, x, y, t, pol, n, true);
 }
 ESVO_API int esvo_ts_push_events(esvo_ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t,
@@ -354,13 +364,13 @@ ESVO_API int esvo_ts_push_events(esvo_ctx* c, int cam, const uint16_t* x, const 
   int rc = esvo_stage_ts_events(c, cam, x, y, t, pol, n);
   if (rc) return rc;
   // the caller's buffers may be reused as soon as we return
-  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_ts));
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_tsc[cam]));
   return ESVO_OK;
 }
 ESVO_API int esvo_run_ts_build(esvo_ctx* c, int cam, int64_t T) {
   CHECK_CTX(c);
   if (cam < 0 || cam > 1) return ESVO_ERR_INVALID_ARG;
-  StreamScope sc(c, c->s_ts);
+  StreamScope sc(c, c->s_tsc[cam]);
   return ts_run_build(c, cam, T);
 }
 ESVO_API int esvo_ts_build(esvo_ctx* c, int cam, int64_t T, int64_t* idx_out, uint8_t* ts_out) {
@@ -368,7 +378,7 @@ ESVO_API int esvo_ts_build(esvo_ctx* c, int cam, int64_t T, int64_t* idx_out, ui
   if (rc) return rc;
   TsState& s = c->ts[cam];
   const DevConsts& d = c->dc;
-  StreamScope sc(c, c->s_ts);
+  StreamScope sc(c, c->s_tsc[cam]);
   if (idx_out) ESVO_CUDA_TRY(c, cudaMemcpyAsync(idx_out, s.out_idx, (size_t)d.W * d.H * 8, cudaMemcpyDeviceToHost, c->stream));
   if (ts_out) ESVO_CUDA_TRY(c, cudaMemcpy2DAsync(ts_out, d.W, s.img_out, d.pitch, d.W, d.H, cudaMemcpyDeviceToHost, c->stream));
   int32_t flags[4] = {0, 0, 0, 0};
@@ -382,7 +392,7 @@ ESVO_API int esvo_ts_reset(esvo_ctx* c, int cam) {
   if (cam < 0 || cam > 1) return ESVO_ERR_INVALID_ARG;
   int rc = drain(c);
   if (rc) return rc;
-  StreamScope sc(c, c->s_ts);
+  StreamScope sc(c, c->s_tsc[cam]);
   return ts_reset_state(c, cam);
 }
 
@@ -430,8 +440,15 @@ ESVO_API int esvo_set_ts_pair_dev(esvo_ctx* c, const double T[16]) {
   // Hand the two freshly built images to the slot WITHOUT copying: swap the slot's observation buffers with
   // the time-surface output buffers.  The buffers the TS state receives in exchange are overwritten by the
   // next build, so the TS stream must first wait until the slot's previous frame stopped reading them.
-  if (sl.ev_free_valid) ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->s_ts, sl.ev_free, 0));
-  ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_obs, c->s_ts));   // both builds of this frame are complete at this point
+  if (c->s_tsc[1] != c->s_tsc[0]) {                              // join the right camera's stream into the left one
+    ESVO_CUDA_TRY(c, cudaEventRecord(c->ev_ts_join, c->s_tsc[1]));
+    ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->s_tsc[0], c->ev_ts_join, 0));
+  }
+  ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_obs, c->s_tsc[0]));    // both builds of this frame are complete at this point
+  if (sl.ev_free_valid) {
+    ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->s_tsc[0], sl.ev_free, 0));
+    if (c->s_tsc[1] != c->s_tsc[0]) ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->s_tsc[1], sl.ev_free, 0));
+  }
   for (int cam = 0; cam < 2; ++cam) {
     TsState& t = c->ts[cam];
     if (t.last_img != t.img_out) { c->set_error("esvo_set_ts_pair_dev: time surface not rebuilt since the last hand-off"); return ESVO_ERR_STATE; }

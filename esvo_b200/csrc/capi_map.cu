@@ -1,6 +1,7 @@
 // esvo_b200 product code -- C ABI, part 2: culling, fusion, map and whole-frame mapping entry points.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -261,14 +262,23 @@ ESVO_API int esvo_results_begin(esvo_ctx* c, int64_t* ticket_out) {
   if (sl.dl_ticket >= 0) { c->set_error("esvo_results_begin: the previous results of this pipeline slot were not collected"); return ESVO_ERR_STATE; }
   const size_t npix = (size_t)c->dc.W * c->dc.H;
   if (!sl.d_dl) {
-    ESVO_CUDA_TRY(c, dmalloc(&sl.d_dl, npix)); ESVO_CUDA_TRY(c, dmalloc(&sl.d_dl_keys, npix)); ESVO_CUDA_TRY(c, dmalloc(&sl.d_dlscal, 4));
-    ESVO_CUDA_TRY(c, cudaMallocHost((void**)&sl.h_dlscal, 8 * 8));
-    ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&sl.ev_dl, cudaEventDisableTiming));
+    // first use: set up the result buffers of EVERY pipeline slot now (pinned allocations take milliseconds each
+    // and must not land in the middle of a running pipeline)
+    for (int i = 0; i < c->depth; ++i) {
+      SlotBufs& q = c->slots[i];
+      if (q.d_dl) continue;
+      ESVO_CUDA_TRY(c, dmalloc(&q.d_dl, npix)); ESVO_CUDA_TRY(c, dmalloc(&q.d_dl_keys, npix)); ESVO_CUDA_TRY(c, dmalloc(&q.d_dlscal, 4));
+      ESVO_CUDA_TRY(c, cudaMallocHost((void**)&q.h_dlscal, 8 * 8));
+      ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&q.ev_dl, cudaEventDisableTiming));
+      // ordered results land here straight from the gather kernels (pinned memory is device-accessible under UVA)
+      q.h_dl_bytes = npix * sizeof(esvo_depth_point);
+      ESVO_CUDA_TRY(c, cudaHostAlloc(&q.h_dl, q.h_dl_bytes, cudaHostAllocDefault));
+    }
   }
   if (!c->s_copy) ESVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
   {
     // right behind this frame's fusion on the slot's own stream
-    int rc = map_gather_async(c, sl.d_dl, sl.d_dl_keys, sl.d_dlscal, sl.h_dlscal);
+    int rc = map_gather_async(c, sl.d_dl, sl.d_dl_keys, sl.d_dlscal, sl.h_dlscal, (esvo_depth_point*)sl.h_dl);
     if (rc) return rc;
     ESVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_counters, sl.d_counters, kCounters * 8, cudaMemcpyDeviceToHost, c->stream));
     ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_dl, c->stream));
@@ -289,24 +299,7 @@ ESVO_API int esvo_results_end(esvo_ctx* c, int64_t ticket, esvo_depth_point* out
     counters[4] = sl.h_dlscal[4]; counters[5] = sl.h_counters[5]; counters[6] = sl.h_counters[6]; counters[7] = sl.h_dlscal[6];
   }
   if (cnt > *n) { *n = cnt; return ESVO_ERR_CAPACITY; }
-  const size_t need = cnt * (sizeof(esvo_depth_point) + 8);
-  if (need > sl.h_dl_bytes) {
-    if (sl.h_dl) cudaFreeHost(sl.h_dl);
-    sl.h_dl_bytes = std::max<size_t>(need * 2, 1 << 20);
-    ESVO_CUDA_TRY(c, cudaMallocHost(&sl.h_dl, sl.h_dl_bytes));
-  }
-  esvo_depth_point* hp = (esvo_depth_point*)sl.h_dl;
-  unsigned long long* hk = (unsigned long long*)(hp + cnt);
-  if (cnt) {
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(hp, sl.d_dl, cnt * sizeof(esvo_depth_point), cudaMemcpyDeviceToHost, c->s_copy));
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(hk, sl.d_dl_keys, cnt * 8, cudaMemcpyDeviceToHost, c->s_copy));
-    ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
-  }
-  // host marshalling: restore the SmartGrid list order (creation sequence)
-  std::vector<uint32_t> ord(cnt);
-  for (size_t i = 0; i < cnt; ++i) ord[i] = (uint32_t)i;
-  std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return hk[a] < hk[b]; });
-  for (size_t i = 0; i < cnt; ++i) out[i] = hp[ord[i]];
+  std::memcpy(out, sl.h_dl, cnt * sizeof(esvo_depth_point));   // already in SmartGrid list order (creation sequence)
   *n = cnt;
   sl.dl_ticket = -1;
   return ESVO_OK;

@@ -325,6 +325,38 @@ __global__ void map_gather_kernel(DevConsts dc, MapSoA M, const double* __restri
   out[pos] = d;
   keys[pos] = M.first_key[pix];
 }
+// ---- ordered hand-off: rank every gathered element by its creation key and write it, in SmartGrid list order,
+// straight into (pinned, device-mapped) host memory.  rank_i = #{ j : key_j < key_i } by brute force over shared
+// memory tiles: n^2 compares, ~20 us for the usual few thousand map points, < 1 ms for a full image.
+__global__ void __launch_bounds__(256) map_rank_permute_kernel(const esvo_depth_point* __restrict__ in,
+                                                               const unsigned long long* __restrict__ keys,
+                                                               const unsigned long long* __restrict__ scal,
+                                                               esvo_depth_point* __restrict__ out) {
+  __shared__ unsigned long long tile[1024];
+  const unsigned n = (unsigned)scal[1];
+  if (blockIdx.x * 256u >= n) return;
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  const unsigned long long my = i < n ? keys[i] : ~0ULL;
+  unsigned rank = 0;
+  for (unsigned base = 0; base < n; base += 1024) {
+    __syncthreads();
+    for (unsigned k = threadIdx.x; k < 1024; k += 256) tile[k] = base + k < n ? keys[base + k] : ~0ULL;
+    __syncthreads();
+    const unsigned m = min(1024u, n - base);
+#pragma unroll 8
+    for (unsigned k = 0; k < m; ++k) rank += tile[k] < my ? 1u : 0u;
+  }
+  // warp-cooperative copy: 29 lanes move the 29 8-byte words of one element at a time (coalesced PCIe writes)
+  constexpr int WORDS = sizeof(esvo_depth_point) / 8;
+  static_assert(sizeof(esvo_depth_point) % 8 == 0 && WORDS <= 32, "element copy assumes <= 32 8-byte words");
+  const unsigned lane = threadIdx.x & 31u, wbase = i - lane;
+  for (unsigned e = 0; e < 32; ++e) {
+    const unsigned r = __shfl_sync(0xffffffffu, rank, e);
+    if (wbase + e < n && lane < WORDS)
+      reinterpret_cast<unsigned long long*>(out + r)[lane] = reinterpret_cast<const unsigned long long*>(in + wbase + e)[lane];
+  }
+}
+
 __global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -480,13 +512,18 @@ int map_regularize(Ctx* c) {
 
 // Enqueue (on c->stream) the compaction of the current map into caller-provided device buffers and the
 // D2H of its scalars: h_scal8[1] = element count, h_scal8[4] = n_fusions, h_scal8[6] = map size.
+// With h_sorted (pinned host memory, npix elements) the elements are also written there in creation order.
 int map_gather_async(Ctx* c, esvo_depth_point* d_out, unsigned long long* d_keys, unsigned long long* d_scal4,
-                     unsigned long long* h_scal8) {
+                     unsigned long long* h_scal8, esvo_depth_point* h_sorted) {
   MapState* ms = c->map;
   const int npix = c->dc.W * c->dc.H, B = 128;
   ESVO_CUDA_TRY(c, cudaMemsetAsync(d_scal4, 0, 32, c->stream));
   map_gather_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->d_T_frame_world + 16, d_out, d_keys, d_scal4);
   c->launches += 1;
+  if (h_sorted) {
+    map_rank_permute_kernel<<<div_up(npix, 256), 256, 0, c->stream>>>(d_out, d_keys, d_scal4, h_sorted);
+    c->launches += 1;
+  }
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(h_scal8, d_scal4, 32, cudaMemcpyDeviceToHost, c->stream));
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(h_scal8 + 4, ms->d_scal, 32, cudaMemcpyDeviceToHost, c->stream));
   ESVO_CUDA_TRY(c, cudaGetLastError());

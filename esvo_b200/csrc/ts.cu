@@ -179,6 +179,94 @@ __global__ void ts_remap_kernel(const uint8_t* __restrict__ src, const float* __
           32 * (32 - fx) * fy * px(ix, iy + 1) + 32 * fx * fy * px(ix + 1, iy + 1);
   dst[(size_t)y * pitch + x] = (uint8_t)((v + (1 << 14)) >> 15);
 }
+// ---- FORWARD mode (TimeSurface.cpp:86-116): every raw pixel splats its decayed value bilinearly onto the four
+// rectified neighbours, each accumulation followed by a clamp at 1.  The reference walks the raw image in raster
+// order, and v <- min(v + w, 1) does not commute, so the result at a destination depends on the ORDER of the
+// sources that reach it (not on anything else).  Same scheme as the depth fusion: (1) one thread per source appends
+// its four contributions to per-destination linked lists (one atomicExch each), node id = 4*source + corner;
+// (2) one thread per destination replays its list in ascending node id = raster order of the sources.
+__global__ void ts_forward_scatter_kernel(const int32_t* __restrict__ scalars, const long long* __restrict__ cur_idx,
+                                          const long long* __restrict__ cur_t, const uint8_t* __restrict__ cur_pol,
+                                          const long long* __restrict__ tmp_idx, const long long* __restrict__ tmp_t,
+                                          const uint8_t* __restrict__ tmp_pol, const int32_t* __restrict__ cnt, int queue_len,
+                                          long long T, double decay_sec, int ignore_polarity, int W, int H,
+                                          const double* __restrict__ lut, long long* __restrict__ out_idx,
+                                          int32_t* head, int32_t* __restrict__ next, double* __restrict__ val) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= W * H) return;
+  const bool general = scalars[2] != 0;
+  long long idx = general ? tmp_idx[p] : cur_idx[p];
+  if (general && idx >= 0 && cnt[p] >= queue_len) idx = -1;   // fell out of the 20-deep queue
+  const long long ts = idx >= 0 ? (general ? tmp_t[p] : cur_t[p]) : 0;
+  if (idx >= 0 && !(ns_to_sec_dev(ts) > 0)) idx = -1;          // :73
+  out_idx[p] = idx;
+  if (idx < 0) return;
+  const double dt = ns_to_sec_dev(T - ts);
+  double e = exp(-dt / decay_sec);                             // :77
+  if (!ignore_polarity) e *= (general ? tmp_pol[p] : cur_pol[p]) ? 1.0 : -1.0;
+  const double u = lut[2 * (size_t)p], v = lut[2 * (size_t)p + 1];
+  if (!(u >= 0 && v >= 0)) return;                             // :89 (NaN fails the test like in the reference)
+  if (u >= (double)W || v >= (double)H) return;                // u_i + 1 < W cannot hold; also keeps floor() in int range
+  const int ui = (int)floor(u), vi = (int)floor(v);
+  if (!(ui + 1 < W && vi + 1 < H)) return;                     // :94
+  const double fu = u - ui, fv = v - vi, fu1 = 1.0 - fu, fv1 = 1.0 - fv;
+  const double w[4] = {fu1 * fv1 * e, fu * fv1 * e, fu1 * fv * e, fu * fv * e};
+  const int dst[4] = {vi * W + ui, vi * W + ui + 1, (vi + 1) * W + ui, (vi + 1) * W + ui + 1};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int node = 4 * p + k;
+    val[node] = w[k];
+    next[node] = atomicExch(&head[dst[k]], node);
+  }
+}
+__global__ void ts_forward_fold_kernel(int W, int H, int pitch, int32_t* head, const int32_t* __restrict__ next,
+                                       const double* __restrict__ val, int ignore_polarity, uint8_t* __restrict__ img) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= W * H) return;
+  const int h = head[p];
+  head[p] = -1;
+  constexpr int CAP = 32;
+  int ids[CAP];
+  int n = 0, total = 0;
+  for (int q = h; q >= 0; q = next[q]) { if (n < CAP) ids[n++] = q; ++total; }
+  double m = 0.0;
+  if (total <= CAP) {
+    for (int a = 1; a < n; ++a) { int v = ids[a], b = a - 1; while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; } ids[b + 1] = v; }
+    for (int a = 0; a < n; ++a) { m += val[ids[a]]; if (m > 1) m = 1; }        // :101-113
+  } else {   // very long list: repeated minimum selection, no storage
+    int last = -1;
+    for (int a = 0; a < total; ++a) {
+      int best = 0x7fffffff;
+      for (int q = h; q >= 0; q = next[q]) if (q > last && q < best) best = q;
+      m += val[best]; if (m > 1) m = 1;
+      last = best;
+    }
+  }
+  const double s = ignore_polarity ? 255.0 * m : 255.0 * (m + 1.0) / 2.0;   // :123-126
+  const int r = __double2int_rn(s);                                         // cvRound, half-to-even
+  const int y = p / W, x = p - y * W;
+  img[(size_t)y * pitch + x] = (uint8_t)min(max(r, 0), 255);
+}
+// cv::medianBlur 3x3 on u8, BORDER_REPLICATE
+__global__ void ts_median3_kernel(const uint8_t* __restrict__ src, int W, int H, int pitch, uint8_t* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  int v[9];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx)
+      v[(dy + 1) * 3 + dx + 1] = src[(size_t)min(max(y + dy, 0), H - 1) * pitch + min(max(x + dx, 0), W - 1)];
+  sort2(v[1], v[2]); sort2(v[4], v[5]); sort2(v[7], v[8]); sort2(v[0], v[1]); sort2(v[3], v[4]); sort2(v[6], v[7]);
+  sort2(v[1], v[2]); sort2(v[4], v[5]); sort2(v[7], v[8]); sort2(v[0], v[3]); sort2(v[5], v[8]); sort2(v[4], v[7]);
+  sort2(v[3], v[6]); sort2(v[1], v[4]); sort2(v[2], v[5]); sort2(v[4], v[7]); sort2(v[4], v[2]); sort2(v[6], v[4]);
+  sort2(v[4], v[2]);
+  dst[(size_t)y * pitch + x] = (uint8_t)v[4];
+}
+__global__ void fill_i32_ts_kernel(int32_t* p, size_t n, int32_t v) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
 __global__ void ts_copy_img_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
@@ -235,7 +323,8 @@ int ts_alloc(Ctx* c, int cam) {
 void ts_free(Ctx* c, int cam) {
   TsState& s = c->ts[cam];
   void* ps[] = {s.ex2, s.ey2, s.et2, s.ep2, s.ex, s.ey, s.et, s.ep, s.cur_idx, s.cur_t, s.cur_pol, s.base_idx, s.base_t, s.base_pol, s.tmp_idx,
-                s.tmp_t, s.tmp_pol, s.cnt, s.out_idx, s.img_med, s.img_out, s.map1, s.map2, s.scalars, s.max_t};
+                s.tmp_t, s.tmp_pol, s.cnt, s.out_idx, s.img_med, s.img_out, s.map1, s.map2, s.scalars, s.max_t,
+                s.fwd_lut, s.fwd_head, s.fwd_next, s.fwd_val};
   for (void* p : ps) if (p) cudaFree(p);
   s = TsState();
 }
@@ -319,27 +408,47 @@ int ts_run_build(Ctx* c, int cam, int64_t T) {
   dim3 blk(TSX, TSY), grd(div_up(d.W, TSX), div_up(d.H, TSY));
   const double decay_sec = c->prm.decay_ms / 1000.0;
   const bool backward = c->prm.time_surface_mode == ESVO_TS_BACKWARD;
-  uint8_t* med_dst = backward ? s.img_med : s.img_out;
   const int ks = c->prm.median_blur_kernel_size > 0 ? 2 * c->prm.median_blur_kernel_size + 1 : 1;
-  if (ks == 3)
-    ts_decay_median_kernel<3><<<grd, blk, 0, c->stream>>>(
-        s.scalars, (const long long*)s.cur_idx, (const long long*)s.cur_t, s.cur_pol, (const long long*)s.tmp_idx,
-        (const long long*)s.tmp_t, s.tmp_pol, s.cnt, c->prm.max_event_queue_len, T, decay_sec, c->prm.ignore_polarity,
-        d.W, d.H, d.pitch, (long long*)s.out_idx, med_dst);
-  else if (ks == 1)
-    ts_decay_median_kernel<1><<<grd, blk, 0, c->stream>>>(
-        s.scalars, (const long long*)s.cur_idx, (const long long*)s.cur_t, s.cur_pol, (const long long*)s.tmp_idx,
-        (const long long*)s.tmp_t, s.tmp_pol, s.cnt, c->prm.max_event_queue_len, T, decay_sec, c->prm.ignore_polarity,
-        d.W, d.H, d.pitch, (long long*)s.out_idx, med_dst);
-  else { c->set_error("median_blur_kernel_size > 1 is not supported on the device path"); return ESVO_ERR_UNSUPPORTED; }
-  c->launches += 1;
+  if (ks != 1 && ks != 3) { c->set_error("median_blur_kernel_size > 1 is not supported on the device path"); return ESVO_ERR_UNSUPPORTED; }
   if (backward) {
+    if (ks == 3)
+      ts_decay_median_kernel<3><<<grd, blk, 0, c->stream>>>(
+          s.scalars, (const long long*)s.cur_idx, (const long long*)s.cur_t, s.cur_pol, (const long long*)s.tmp_idx,
+          (const long long*)s.tmp_t, s.tmp_pol, s.cnt, c->prm.max_event_queue_len, T, decay_sec, c->prm.ignore_polarity,
+          d.W, d.H, d.pitch, (long long*)s.out_idx, s.img_med);
+    else
+      ts_decay_median_kernel<1><<<grd, blk, 0, c->stream>>>(
+          s.scalars, (const long long*)s.cur_idx, (const long long*)s.cur_t, s.cur_pol, (const long long*)s.tmp_idx,
+          (const long long*)s.tmp_t, s.tmp_pol, s.cnt, c->prm.max_event_queue_len, T, decay_sec, c->prm.ignore_polarity,
+          d.W, d.H, d.pitch, (long long*)s.out_idx, s.img_med);
     dim3 b2(32, 8), g2(div_up(d.W, 32), div_up(d.H, 8));
     ts_remap_kernel<<<g2, b2, 0, c->stream>>>(s.img_med, s.map1, s.map2, d.W, d.H, d.pitch, s.img_out);
-    c->launches += 1;
+    c->launches += 2;
   } else {
-    c->set_error("FORWARD time-surface mode is not implemented on the device path yet");
-    return ESVO_ERR_UNSUPPORTED;
+    // FORWARD: the splat itself rectifies, no remap afterwards (TimeSurface.cpp:138-142 publishes the image as is)
+    if (!s.fwd_lut) {
+      ESVO_CUDA_TRY(c, dmalloc(&s.fwd_lut, 2 * npix)); ESVO_CUDA_TRY(c, dmalloc(&s.fwd_head, npix));
+      ESVO_CUDA_TRY(c, dmalloc(&s.fwd_next, 4 * npix)); ESVO_CUDA_TRY(c, dmalloc(&s.fwd_val, 4 * npix));
+      fill_i32_ts_kernel<<<div_up((int)npix, B), B, 0, c->stream>>>(s.fwd_head, npix, -1);
+      c->launches += 1;
+    }
+    if (s.fwd_tables_version != c->tables_version) {
+      ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.fwd_lut, c->cam[cam].lut.data(), 2 * npix * 8, cudaMemcpyHostToDevice, c->stream));
+      ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // pageable source
+      s.fwd_tables_version = c->tables_version;
+    }
+    ts_forward_scatter_kernel<<<div_up((int)npix, B), B, 0, c->stream>>>(
+        s.scalars, (const long long*)s.cur_idx, (const long long*)s.cur_t, s.cur_pol, (const long long*)s.tmp_idx,
+        (const long long*)s.tmp_t, s.tmp_pol, s.cnt, c->prm.max_event_queue_len, T, decay_sec, c->prm.ignore_polarity, d.W, d.H,
+        s.fwd_lut, (long long*)s.out_idx, s.fwd_head, s.fwd_next, s.fwd_val);
+    ts_forward_fold_kernel<<<div_up((int)npix, B), B, 0, c->stream>>>(d.W, d.H, d.pitch, s.fwd_head, s.fwd_next, s.fwd_val,
+                                                                     c->prm.ignore_polarity, ks == 3 ? s.img_med : s.img_out);
+    c->launches += 2;
+    if (ks == 3) {
+      dim3 b2(32, 8), g2(div_up(d.W, 32), div_up(d.H, 8));
+      ts_median3_kernel<<<g2, b2, 0, c->stream>>>(s.img_med, d.W, d.H, d.pitch, s.img_out);
+      c->launches += 1;
+    }
   }
   c->prof_end(pe);
   ESVO_CUDA_TRY(c, cudaGetLastError());

@@ -146,3 +146,36 @@ def test_kat_zncc_cost(oracle_lib):
     assert abs(f(ptr(p), ptr(q), C.c_size_t(105)) - 1.0) < 1e-7
     flat = np.full(105, 7.0)
     assert abs(f(ptr(flat), ptr(p), C.c_size_t(105)) - 0.5) < 1e-12   # zero variance -> correlation 0
+
+
+def test_oracle_forward_time_surface_against_numpy(oracle_lib):
+    """FORWARD mode of createTimeSurfaceAtTime (TimeSurface.cpp:86-116) restated independently in numpy:
+    raster-order bilinear splat of exp(-dt/tau) with a clamp at 1 after every accumulation."""
+    from util import scenario
+    l, r = configs.rig_calibs("hkust")
+    p = configs.params_for("hkust", oracle_lib)
+    p.time_surface_mode = 1; p.median_blur_kernel_size = 0
+    o = capi.Backend(oracle_lib, l, r, p)
+    s = scenario("hkust"); e = s["left"]
+    o.ts_push_events(0, e["x"], e["y"], e["t"], e["p"])
+    T = s["t_ts_ns"]
+    idx, img = o.ts_build(0, T)
+    _, _, lut, _ = o.get_rectify_tables(0)
+    W, H = 346, 260
+    idx = np.asarray(idx).reshape(-1); lut = np.asarray(lut).reshape(-1, 2)
+    mp = np.zeros((H, W))
+    for pix in np.nonzero(idx >= 0)[0]:                      # ascending = raster order
+        ev = np.exp(-((T - int(e["t"][idx[pix]])) * 1e-9) / 0.03)
+        u, v = lut[pix]
+        if not (u >= 0 and v >= 0):
+            continue
+        ui, vi = int(np.floor(u)), int(np.floor(v))
+        if not (ui + 1 < W and vi + 1 < H):
+            continue
+        fu, fv = u - ui, v - vi
+        for yy, xx, w in ((vi, ui, (1 - fu) * (1 - fv)), (vi, ui + 1, fu * (1 - fv)), (vi + 1, ui, (1 - fu) * fv), (vi + 1, ui + 1, fu * fv)):
+            mp[yy, xx] = min(mp[yy, xx] + w * ev, 1.0)
+    ref = np.clip(np.rint(255 * mp), 0, 255).astype(np.uint8)
+    img = np.asarray(img).reshape(H, W)
+    assert (img == 255).sum() > 100                           # the clamp is exercised
+    assert np.abs(ref.astype(int) - img.astype(int)).max() <= 1 and (ref != img).mean() < 1e-3
