@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turns the ncu artefacts a gpurun call brought back (gpurun_out/) into the tracked summaries under profiles/.
-usage: python scripts/summarize_ncu.py <round-tag> <launches.csv> <full.ncu-rep>"""
+usage: python scripts/summarize_ncu.py <round-tag> <launches.csv> <full.ncu-rep> [launch-list command] [full-capture command]"""
 import csv
 import os
 import subprocess
@@ -9,6 +9,8 @@ from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+cmd_launches = sys.argv[4] if len(sys.argv) > 4 else "ncu --metrics gpu__time_duration.sum --clock-control none -s <skip> -c 400 --csv python bench.py --steps 12 --warmup 3 --no-cpu-baseline"
+cmd_full = sys.argv[5] if len(sys.argv) > 5 else "ncu --set full --clock-control none --import-source on -k regex:<kernels> -s <skip> -c <n> python bench.py --steps 12 --warmup 3 --no-cpu-baseline"
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
@@ -21,7 +23,7 @@ for r in rows:
     a[0] += 1; a[1] += float(r[14])
 tot = sum(v[1] for v in agg.values())
 lines = [f"# ncu launch list, {tag}", "",
-         "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline`",
+         f"Command: `{cmd_launches}`",
          f"({len(rows)} launches captured after the priming/warm-up frames; per-launch times are cold-cache and serialised: compare SHARES)", "",
          "| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -43,7 +45,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
 idx = {h: i for i, h in enumerate(hdr)}
 units = rr[1]
 lines = [f"# ncu --set full, {tag}", "",
-         "Command: `ncu --set full --clock-control none --import-source on -k regex:\"lm_kernel|bm_kernel|fuse_fold_kernel|ts_decay_median\" -s 100 -c 4 python bench.py --steps 3 --warmup 3 --no-cpu-baseline`",
+         f"Command: `{cmd_full}`",
          "", "traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch.", ""]
 for r in rr[2:]:
     if len(r) < len(hdr):
