@@ -27,7 +27,9 @@ struct MapSoA {
   int32_t *row, *col;
   unsigned long long* first_key;
 };
+struct FoldRec { double rho, s2, nu, var, res, sd2; };   // what the fold reads per contribution; sd2 = 2*sqrt(var)
 struct PropSoA {  // propagated points staged for the current fold
+  FoldRec* hot;
   uint8_t* ok;
   double *rho, *s2, *nu, *var, *res, *x0, *x1, *pc0, *pc1, *pc2;
   long long* age;
@@ -118,6 +120,7 @@ __global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, const double* __res
   }
   P.pc0[sid] = pp[0]; P.pc1[sid] = pp[1]; P.pc2[sid] = pp[2];
   P.res[sid] = d.residual; P.age[sid] = d.age;
+  { FoldRec r; r.rho = invDepth; r.s2 = P.s2[sid]; r.nu = P.nu[sid]; r.var = P.var[sid]; r.res = d.residual; r.sd2 = 2 * sqrt(r.var); P.hot[sid] = r; }
   const int lo = radius == 0 ? 0 : -1;
   int i = 0;
   for (int dy = lo; dy <= 1; ++dy)
@@ -153,15 +156,21 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
     fkey = M.first_key[pix];
   }
   int nfus = 0;
-  auto apply = [&](int cid) {
+  // p_cam is overwritten by every create / fuse step and never read back by the recurrence, so it is evaluated
+  // once at the end from the inverse depth that set it last (pc_rho); a replacement copies the propagated p_cam.
+  bool pc_pending = false;
+  double pc_rho = 0;
+  double sdm = ex ? 2 * sqrt(var) : 0.0;          // 2*sqrt(var) of the map point, refreshed whenever var changes
+  auto apply = [&](int cid, const FoldRec& r) {
     const int sid = cid / 9;
-    const double prho = P.rho[sid], ps2 = P.s2[sid], pnu = P.nu[sid], pvar = P.var[sid], pres = P.res[sid];
+    const double prho = r.rho, ps2 = r.s2, pnu = r.nu, pvar = r.var, pres = r.res;
     if (!ex) {  // case 1 (:126-145)
       ex = true; erow = row; ecol = col; x0 = col + 0.5; x1 = row + 0.5;
       rho = prho; var = pvar; s2 = ps2; nu = pnu;
       if (dc.lsnorm == ESVO_LSNORM_L2 && var < 1e-6) var = 1e-6;
+      sdm = (dc.lsnorm == ESVO_LSNORM_L2) ? 2 * sqrt(var) : r.sd2;
       res = pres; age = P.age[sid];
-      cam2world_f(dc, x0, x1, prho, pc0, pc1, pc2);
+      pc_rho = prho; pc_pending = true;
       fkey = seq_base + (unsigned long long)cid;
       return;
     }
@@ -171,7 +180,7 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
       compat = (d2 / pvar + d2 / var) < 5.99;
     } else {
       const double diff = fabs(prho - rho);
-      compat = diff < 2 * sqrt(pvar) || diff < 2 * sqrt(var);
+      compat = diff < r.sd2 || diff < sdm;
     }
     if (compat) {  // case 2.1 (:162-177)
       if (dc.lsnorm == ESVO_LSNORM_L2) {
@@ -189,15 +198,18 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
         var = nu / (nu - 2) * s2;
         age++;                                   // DepthPoint.cpp:179
       }
+      sdm = 2 * sqrt(var);
       age++;                                     // DepthFusion.cpp:171
       res = fmin(res, pres);
-      cam2world_f(dc, x0, x1, prho, pc0, pc1, pc2);   // p_cam from the PROPAGATED rho (:174)
+      pc_rho = prho; pc_pending = true;          // p_cam from the PROPAGATED rho (:174)
       nfus++;
     } else {       // case 2.2 (:178-188)
-      if (rho - 2 * sqrt(var) > prho) return;
+      if (rho - sdm > prho) return;
       if (pvar < var && pres < res) {              // dm->get(row,col) = dp_prop
         rho = prho; s2 = ps2; nu = pnu; var = pvar; res = pres; age = P.age[sid];
+        sdm = r.sd2;
         x0 = P.x0[sid]; x1 = P.x1[sid]; pc0 = P.pc0[sid]; pc1 = P.pc1[sid]; pc2 = P.pc2[sid];
+        pc_pending = false;
         erow = P.row[sid]; ecol = P.col[sid];
       }
     }
@@ -220,16 +232,23 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
       for (int st = (cnt - 2) / 2; st >= 0; --st) sift(st, cnt - 1);
       for (int end = cnt - 1; end > 0; --end) { int tmp = ids[end]; ids[end] = ids[0]; ids[0] = tmp; sift(0, end - 1); }
     }
-    for (int a = 0; a < cnt; ++a) apply(ids[a]);
+    FoldRec cur = P.hot[ids[0] / 9];
+    for (int a = 0; a < cnt; ++a) {              // the next record is in flight while this one is folded
+      FoldRec nxt = cur;
+      if (a + 1 < cnt) nxt = P.hot[ids[a + 1] / 9];
+      apply(ids[a], cur);
+      cur = nxt;
+    }
   } else {  // long list: repeated minimum selection, O(L^2) walks, no storage
     int last = -1;
     for (int a = 0; a < total; ++a) {
       int best = 0x7fffffff;
       for (int q = h; q >= 0; q = next[q]) if (q > last && q < best) best = q;
-      apply(best);
+      apply(best, P.hot[best / 9]);
       last = best;
     }
   }
+  if (pc_pending) cam2world_f(dc, x0, x1, pc_rho, pc0, pc1, pc2);
   M.exists[pix] = ex ? 1 : 0;
   M.rho[pix] = rho; M.s2[pix] = s2; M.nu[pix] = nu; M.var[pix] = var; M.res[pix] = res; M.x0[pix] = x0; M.x1[pix] = x1;
   M.pc0[pix] = pc0; M.pc1[pix] = pc1; M.pc2[pix] = pc2; M.age[pix] = age; M.row[pix] = erow; M.col[pix] = ecol;
@@ -369,9 +388,9 @@ static int prop_reserve(Ctx* c, size_t need) {
   if (ms->staged) { c->set_error("internal: staging buffer grown while points are staged"); return ESVO_ERR_STATE; }
   size_t cap = std::max<size_t>(need, 65536);
   PropSoA& P = ms->p;
-  void* olds[] = {P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col, ms->next};
+  void* olds[] = {P.hot, P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col, ms->next};
   for (void* p : olds) if (p) cudaFree(p);
-  ESVO_CUDA_TRY(c, dm(&P.ok, cap));
+  ESVO_CUDA_TRY(c, dm(&P.ok, cap)); ESVO_CUDA_TRY(c, dm(&P.hot, cap));
   double** ds[] = {&P.rho, &P.s2, &P.nu, &P.var, &P.res, &P.x0, &P.x1, &P.pc0, &P.pc1, &P.pc2};
   for (double** d : ds) ESVO_CUDA_TRY(c, dm(d, cap));
   ESVO_CUDA_TRY(c, dm(&P.age, cap)); ESVO_CUDA_TRY(c, dm(&P.row, cap)); ESVO_CUDA_TRY(c, dm(&P.col, cap));
@@ -410,7 +429,7 @@ void fuse_free(Ctx* c) {
   if (!ms) return;
   MapSoA& M = ms->m; PropSoA& P = ms->p;
   void* ps[] = {M.exists, M.rho, M.s2, M.nu, M.var, M.res, M.x0, M.x1, M.pc0, M.pc1, M.pc2, M.rho_tmp, M.age, M.row, M.col,
-                M.first_key, P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col,
+                M.first_key, P.hot, P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col,
                 ms->head, ms->next, ms->d_T_frame_world, ms->d_dl, ms->d_dl_keys, ms->d_scal};
   for (void* p : ps) if (p) cudaFree(p);
   if (ms->h_scal) cudaFreeHost(ms->h_scal);
