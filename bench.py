@@ -35,6 +35,8 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 BM_BYTES = 420.0          # 105 px x 4 B per BM candidate (f32 TS convention)
+NCU_TRAFFIC_BYTES = {"lm_kernel": 730624, "bm_kernel": 720128}   # profiles/r1_full_summary.md
+LM_FP64_FLOPS_PER_EVAL = 32980                                        # 1.605 GFLOP / 48 668 evaluations (same capture)
 LM_BYTES = 1024.0         # 2 x (15+1)(7+1) px x 4 B per LM residual evaluation
 N_SEEDS = 5000
 RIG = "hkust"
@@ -379,9 +381,19 @@ def run_ours(args, rank, world, local_rank):
                "ms_per_launch": bm_ms, "algorithmic_bytes_per_launch": bm_bytes, "traffic": None}
     lm_roof = {"kernel": "lm_kernel", "bound": "hbm", "achieved": lm_bytes / (lm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                "ms_per_launch": lm_ms, "algorithmic_bytes_per_launch": lm_bytes, "traffic": None}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
+    # (profiles/r1_full_summary.md): the TS pair is L1/L2-resident, DRAM traffic is ~1.5 % of the algorithmic bytes
+    bm_roof["traffic"], lm_roof["traffic"] = NCU_TRAFFIC_BYTES["bm_kernel"], NCU_TRAFFIC_BYTES["lm_kernel"]
     for rf in (bm_roof, lm_roof):
         rf["frac"] = rf["achieved"] / peak
         rf["peak_kind"] = peak_kind
+    # What actually bounds the dominant kernel: dependent FP64 issue.  FP64 operations per executed evaluation were
+    # counted with ncu (thread-level DFMA x2 + DMUL + DADD of the same capture); the rate below is live, over the
+    # whole timed region (all pipeline slots), against the nominal FP64 peak 148 SM x 64 lanes x 2 x 1.965 GHz.
+    fp64 = {"flops_per_eval": LM_FP64_FLOPS_PER_EVAL, "achieved_tflops": lm_exec * LM_FP64_FLOPS_PER_EVAL * K / (total_ms * 1e-3) / 1e12,
+            "peak_tflops": 148 * 64 * 2 * 1.965e9 / 1e12, "peak_kind": "nominal"}
+    fp64["frac"] = fp64["achieved_tflops"] / fp64["peak_tflops"]
+    lm_roof["fp64"] = fp64
     dom, other = (lm_roof, bm_roof) if lm_ms >= bm_ms else (bm_roof, lm_roof)
     out = {
         "metric": "depth-candidate patch evals/s (EventBM zncc + DepthProblem LM) @346x260, 5k seeds/frame",

@@ -18,6 +18,28 @@ int main() {
   if (st.size() != 201) bad |= 16;                                             // 10 ms window / 50 us
   if (!st.empty() && (st.front() != t_end - 10000000 || st.back() > t_end)) bad |= 32;
   if (fromSec(toSec(1234567891234567890LL)) / 1000 != 1234567891234567890LL / 1000) bad |= 64;
+  // denoising: a 3x3 block of events survives entirely only in its centre; an isolated event never does
+  {
+    std::vector<esvo::Event> ev2; std::vector<esvo::Event*> all, close, kept;
+    for (int dy = 0; dy < 3; ++dy) for (int dx = 0; dx < 3; ++dx) ev2.push_back({(uint16_t)(50 + dx), (uint16_t)(40 + dy), 1, true});
+    ev2.push_back({200, 100, 2, true});                       // isolated
+    for (int dx = 0; dx < 3; ++dx) for (int dy = 0; dy < 2; ++dy) ev2.push_back({(uint16_t)dx, (uint16_t)dy, 3, true});  // 3x2 block at the corner (borders replicate)
+    for (auto& e : ev2) { all.push_back(&e); close.push_back(&e); }
+    std::vector<uint8_t> mask;
+    createDenoisingMask(all, mask, 260, 346);
+    if (mask[41 * 346 + 51] != 255 || mask[100 * 346 + 200] != 0) bad |= 128;
+    if (mask[0] != 255) bad |= 256;                            // corner pixel: replicated border makes 6 of 9 neighbours set
+    int on = 0; for (uint8_t m : mask) on += m == 255;
+    extractDenoisedEvents(close, kept, mask, 346, 4);
+    if (kept.size() != 4) bad |= 512;                          // maxNum honoured, arrival order kept
+    for (auto* e : kept) if (mask[(size_t)e->y * 346 + e->x] != 255) bad |= 1024;
+    std::vector<esvo::DepthPoint> el(2); el[0].p_cam[0] = 1; el[0].p_cam[1] = 2; el[0].p_cam[2] = 3; el[1].p_cam[0] = 0; el[1].p_cam[1] = 0; el[1].p_cam[2] = 10;
+    esvo::Pose T = {0, -1, 0, 5, 1, 0, 0, 6, 0, 0, 1, 7, 0, 0, 0, 1};
+    std::vector<float> xyz, nearp;
+    packPointCloud(el, T, xyz, &nearp, 5.0);
+    if (xyz.size() != 6 || xyz[0] != 3.f || xyz[1] != 7.f || xyz[2] != 10.f || nearp.size() != 3) bad |= 2048;
+    (void)on;
+  }
   std::printf("frontend check %s (flags %d): %zu events, %zu stamps\n", bad ? "FAILED" : "ok", bad, sel.size(), st.size());
   return bad;
 }

@@ -276,6 +276,50 @@ inline std::vector<int64_t> samplePoseStamps(int64_t t_end_ns, double BM_half_sl
   while (toSec(t_tmp) <= t_end) { out.push_back(t_tmp); t_tmp = fromSec(toSec(t_tmp) + 0.05 * BM_half_slice_thickness); }
   return out;
 }
+//  * createDenoisingMask / extractDenoisedEvents (esvo_Mapping.cpp:1046-1072, bDenoising_): binary event map of ALL
+//    window events -> cv::medianBlur 3x3 (on a 0/255 image: a pixel survives iff at least 5 of its 3x3 neighbours,
+//    borders replicated, carry an event) -> keep the close events that sit on surviving pixels, at most maxNum.
+inline void createDenoisingMask(const std::vector<esvo::Event*>& vAllEventsPtr, std::vector<uint8_t>& mask, size_t row, size_t col) {
+  std::vector<uint8_t> eventMap(row * col, 0);                       // Visualization::plot_eventMap (Visualization.cpp:96-104)
+  for (const esvo::Event* e : vAllEventsPtr) if (e->x < col && e->y < row) eventMap[(size_t)e->y * col + e->x] = 255;
+  mask.assign(row * col, 0);
+  for (size_t y = 0; y < row; ++y)
+    for (size_t x = 0; x < col; ++x) {
+      int on = 0;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const size_t yy = (size_t)std::min<long>(std::max<long>((long)y + dy, 0), (long)row - 1);
+          const size_t xx = (size_t)std::min<long>(std::max<long>((long)x + dx, 0), (long)col - 1);
+          on += eventMap[yy * col + xx] != 0;
+        }
+      mask[y * col + x] = on >= 5 ? 255 : 0;
+    }
+}
+inline void extractDenoisedEvents(const std::vector<esvo::Event*>& vCloseEventsPtr, std::vector<esvo::Event*>& vEdgeEventsPtr,
+                                  const std::vector<uint8_t>& mask, size_t col, size_t maxNum) {
+  vEdgeEventsPtr.reserve(vCloseEventsPtr.size());
+  for (esvo::Event* e : vCloseEventsPtr) {
+    if (vEdgeEventsPtr.size() >= maxNum) break;
+    if (mask[(size_t)e->y * col + e->x] == 255) vEdgeEventsPtr.push_back(e);
+  }
+}
+//  * the local-map hand-off of publishPointCloud (esvo_Mapping.cpp:909-953): p_world = R p_cam + t as pcl::PointXYZ
+//    (f32 x,y,z) in DepthMap iteration order; `near` additionally keeps ||p_cam|| < visualize_range (:930-931).
+//    The result is what RefFrame::vPointXYZ_ / esvo_track_reset consume on the tracking side (esvo_Tracking.cpp:202-234).
+inline void packPointCloud(const std::vector<esvo::DepthPoint>& elems, const esvo::Pose& T_world_result, std::vector<float>& xyz,
+                           std::vector<float>* xyz_near = nullptr, double visualize_range = 0.0) {
+  xyz.clear(); xyz.reserve(3 * elems.size());
+  if (xyz_near) xyz_near->clear();
+  const double* T = T_world_result.data();
+  for (const esvo::DepthPoint& d : elems) {
+    const double* p = d.p_cam;
+    const double w[3] = {T[0] * p[0] + T[1] * p[1] + T[2] * p[2] + T[3], T[4] * p[0] + T[5] * p[1] + T[6] * p[2] + T[7],
+                         T[8] * p[0] + T[9] * p[1] + T[10] * p[2] + T[11]};
+    for (int k = 0; k < 3; ++k) xyz.push_back((float)w[k]);
+    if (xyz_near && std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]) < visualize_range)
+      for (int k = 0; k < 3; ++k) xyz_near->push_back((float)w[k]);
+  }
+}
 }  // namespace frontend
 
 // esvo_core::esvo_Mapping::MappingAtTime (esvo_Mapping.cpp:261-399) as one call with device-resident hand-off.

@@ -110,3 +110,14 @@ def test_equidistant_rectification_tables_match_cv2_fisheye(oracle_lib):
         mk = (cv2.remap(ones, r1, r2, cv2.INTER_LINEAR) > 0.1).astype(np.uint8) * 255
         assert (mask != mk).mean() < 1e-3
     assert abs(b.get_derived()["baseline"] - 19.941771812941038 / 199.6530123165822) < 1e-12
+
+
+def test_denoising_mask_rule_matches_cv2_median():
+    """esvo_core::frontend::createDenoisingMask (shim) uses 'at least 5 of the 3x3 neighbours, borders replicated';
+    that IS cv::medianBlur(eventMap, mask, 3) on a 0/255 image (esvo_Mapping.cpp:1046-1054)."""
+    rng = np.random.default_rng(3)
+    img = (rng.random((260, 346)) < 0.35).astype(np.uint8) * 255
+    ref = cv2.medianBlur(img, 3)
+    pad = np.pad(img // 255, 1, mode="edge").astype(np.int32)
+    cnt = sum(pad[dy:dy + 260, dx:dx + 346] for dy in range(3) for dx in range(3))
+    assert np.array_equal(ref, np.where(cnt >= 5, 255, 0).astype(np.uint8))
