@@ -182,7 +182,12 @@ def run_ours(args, rank, world, local_rank):
     while not sampler.rows and time.time() - t_wait < 15:     # nvidia-smi start-up is over once the first row arrives
         time.sleep(0.05)
     from esvo_b200 import dist as _ed
-    base = make_workload(seed=_ed.stream_seed(rank))
+    # Weak scaling needs the same work on every GPU: by default every rank replays the SAME synthetic stream shape (scene
+    # seed 10; stream id and time origin differ per rank).  --streams distinct gives every rank its own scene
+    # (seeds 10, 11, ... as in SURVEY cfg 5); per-frame work then differs by up to ~30 % and the step time is the slowest stream's.
+    base = make_workload(seed=_ed.stream_seed(rank if args.streams == "distinct" else 0))
+    if args.streams != "distinct" and rank:
+        base = shifted(base, 1000 * rank)
     K, Wm = args.steps, args.warmup
     NP = prm.max_num_fusion_frames
     KP = min(K, 48)                         # steps of the separately profiled pass (per-stage breakdown)
@@ -365,7 +370,9 @@ def run_ours(args, rank, world, local_rank):
     from esvo_b200 import dist as edist
     m_last = g.map_download()
     rec = edist.make_record(edist.stream_seed(rank), K, ce, edist.map_checksum(m_last))
+    per_rank_local = total_ms / K
     total_ms, evals_all, records = edist.reduce_and_gather(total_ms, float(evals_step), rec, device="cuda")
+    per_rank = edist.gather_scalars([per_rank_local, e2e_s * 1e3 / K, float(np.mean(np.diff(issue_t)) * 1e3)], device="cuda")
     e2e_ms, e2e_evals_all, _ = edist.reduce_and_gather(e2e_s * 1e3, float(e2e_evals), rec, device="cuda")
     if rank != 0:
         return
@@ -405,6 +412,7 @@ def run_ours(args, rank, world, local_rank):
                                "20-frame window fusion + clean + regularise",
                    "seeds_per_frame": N_SEEDS, "events_per_frame_per_camera": int(base["left"]["x"].size),
                    "parallelism": f"{world} independent streams, one per GPU, no data-path collective",
+                   "streams": "every GPU runs the same synthetic stream shape (equal work per GPU)" if args.streams == "same" else "distinct scenes per GPU (seeds 10..)",
                    "l2": "inputs larger than L2, read once: every timed step consumes its own event/seed/pose arrays (1.75 MB per step, "
                          "all evicted by a 256 MiB write right before the timed region; with software-pipelined frames in flight a flush "
                          "between iterations would serialise the pipeline); the persistent state (TS images, LUT, grids, ~6 MB) is "
@@ -425,6 +433,8 @@ def run_ours(args, rank, world, local_rank):
                      "n_seeds": ctr["n_seeds"], "n_solved": ctr["n_solved"], "n_culled": ctr["n_culled"],
                      "n_fusions": ctr["n_fusions"], "map_size": ctr["map_size"]},
         "wall_s_timed_region": t_wall,
+        "per_rank_ms_per_step": {"resident": [float(v) for v in per_rank[:, 0]], "e2e": [float(v) for v in per_rank[:, 1]],
+                                 "host_issue_resident": [float(v) for v in per_rank[:, 2]]},
         # host-side time per step() call (enqueue only; large values = the submission queue was full or the host stalled)
         "host_issue_ms": {leg: {"mean": float(np.mean(np.diff(t)) * 1e3), "p99": float(np.percentile(np.diff(t), 99) * 1e3),
                                 "max": float(np.max(np.diff(t)) * 1e3)} for leg, t in (("resident", issue_t), ("e2e", issue_e))},
@@ -433,6 +443,15 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_leg(base, sample_steps=3)
     print(json.dumps(out))
+
+
+def _shutdown_pg():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def cpu_leg(base, sample_steps, threads=None):
@@ -494,15 +513,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", default="same", choices=["same", "distinct"], help="per-GPU synthetic streams: same shape (equal work) or distinct scenes")
     ap.add_argument("--pipeline-depth", type=int, default=16, help="frames in flight per stream (1 = strictly sequential)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_ours(args, rank, world, local_rank)
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        else:
+            run_ours(args, rank, world, local_rank)
+    finally:
+        _shutdown_pg()
 
 
 if __name__ == "__main__":

@@ -118,7 +118,6 @@ int slot_alloc(Ctx* c, int i) {
 int drain(Ctx* c) {
   for (int k = 0; k < 2; ++k) if (c->s_tsc[k]) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_tsc[k]));
   for (int i = 0; i < kMaxSlots; ++i) {
-    if (c->slots[i].lm_stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->slots[i].lm_stream));
     if (c->slots[i].stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->slots[i].stream));
   }
   if (c->s_copy) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
@@ -299,9 +298,6 @@ ESVO_API void esvo_destroy(esvo_ctx* c) {
     if (s.d_dlscal) cudaFree(s.d_dlscal);
     if (s.h_dlscal) cudaFreeHost(s.h_dlscal);
     if (s.h_dl) cudaFreeHost(s.h_dl);
-    if (s.lm_stream) cudaStreamDestroy(s.lm_stream);
-    if (s.ev_seeds) cudaEventDestroy(s.ev_seeds);
-    if (s.ev_lm) cudaEventDestroy(s.ev_lm);
     if (s.stream && s.stream != c->s_main) cudaStreamDestroy(s.stream);
   }
   for (auto& f : c->win) { cudaFree(f.pts); cudaFree(f.cnt); if (f.last_read) cudaEventDestroy(f.last_read); }

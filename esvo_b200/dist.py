@@ -44,3 +44,16 @@ def reduce_and_gather(local_ms: float, local_evals: float, record: np.ndarray, d
     out = [torch.empty_like(rec) for _ in range(dist.get_world_size())]
     dist.all_gather(out, rec)
     return float(t.item()), float(e.item()), np.stack([o.cpu().numpy() for o in out])
+
+
+def gather_scalars(values, device="cpu"):
+    """All-gather a short list of floats; returns an array [world, len(values)] on every rank (diagnostics)."""
+    import torch
+    import torch.distributed as dist
+    v = np.asarray(values, np.float64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return v[None, :].copy()
+    t = torch.from_numpy(v.copy()).to(device)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return np.stack([o.cpu().numpy() for o in out])
