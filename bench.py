@@ -442,6 +442,11 @@ def run_ours(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_leg(base, sample_steps=3)
+        # the same port in the reference's own thread configuration (NUM_THREAD_TS 1, NUM_THREAD_MAPPING 4: TimeSurface.h:25,
+        # tools/utils.h:35-36), one frame
+        ref4 = cpu_leg(base, sample_steps=1, threads=4)
+        out["cpu_baseline"]["reference_thread_config"] = {"value": ref4["value"], "unit": "evals/s", "cores": 4,
+                                                           "ms_per_step": ref4["ms_per_step"], "sample": "1 mapping frame, BM+LM on 4 threads"}
     print(json.dumps(out))
 
 

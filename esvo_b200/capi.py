@@ -360,6 +360,25 @@ class Backend:
         keys = ["n_events", "n_seeds", "n_solved", "n_culled", "n_fusions", "bm_evals", "lm_evals", "map_size"]
         return dict(zip(keys, [int(v) for v in ctr]))
 
+    def init_from_disparity(self, disp16, ex, ey, T_world_left, min_points):
+        """InitializationAtTime downstream of the SGM call: returns (number of SGM depth points, accepted)."""
+        d = _arr(disp16, np.int16); x = _arr(ex, np.uint16); y = _arr(ey, np.uint16)
+        T = np.ascontiguousarray(T_world_left, np.float64)
+        assert d.size == self.W * self.H
+        n = C.c_size_t(0); acc = C.c_int(0)
+        self._call("init_from_disparity",
+                   [C.POINTER(C.c_int16), C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.c_size_t, C.POINTER(C.c_double), C.c_size_t,
+                    C.POINTER(C.c_size_t), C.POINTER(C.c_int)],
+                   _ptr(d, C.c_int16), _ptr(x, C.c_uint16), _ptr(y, C.c_uint16), x.size, _ptr(T, C.c_double), int(min_points),
+                   C.byref(n), C.byref(acc))
+        return int(n.value), bool(acc.value)
+
+    def window_download(self, index):
+        out = np.zeros(self.W * self.H, DEPTH_POINT_DTYPE)
+        n = C.c_size_t(out.size)
+        self._call("window_download", [C.c_int, C.c_void_p, C.POINTER(C.c_size_t)], int(index), out.ctypes.data_as(C.c_void_p), C.byref(n))
+        return out[: n.value].copy()
+
     def set_pipeline_depth(self, depth):
         self._call("set_pipeline_depth", [C.c_int], int(depth))
 

@@ -207,6 +207,59 @@ ESVO_API int esvo_map_download(esvo_ctx* c, esvo_depth_point* out, size_t* n) {
   if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }
   return map_download(c, out, n);
 }
+ESVO_API int esvo_init_from_disparity(esvo_ctx* c, const int16_t* disp16, const uint16_t* ex, const uint16_t* ey, size_t n,
+                                      const double T[16], size_t min_points, size_t* n_points, int* accepted) {
+  CHECK_CTX(c);
+  if (!disp16 || !T || (n && (!ex || !ey))) return ESVO_ERR_INVALID_ARG;
+  { int rc0 = drain(c); if (rc0) return rc0; }                     // a one-off at start-up: strictly synchronous
+  const size_t npix = (size_t)c->dc.W * c->dc.H;
+  int16_t* d_disp = nullptr; uint16_t *d_x = nullptr, *d_y = nullptr;
+  Ctx::WinFrame f;
+  int rc = win_acquire(c, std::max<size_t>(n, 1), f);
+  if (rc) return rc;
+  auto cleanup = [&]() { cudaFree(d_disp); cudaFree(d_x); cudaFree(d_y); };
+  if (dmalloc(&d_disp, npix) || dmalloc(&d_x, n) || dmalloc(&d_y, n)) { cleanup(); c->win_pool.push_back(f); return ESVO_ERR_CUDA; }
+  cudaMemcpyAsync(d_disp, disp16, npix * 2, cudaMemcpyHostToDevice, c->stream);
+  if (n) { cudaMemcpyAsync(d_x, ex, n * 2, cudaMemcpyHostToDevice, c->stream); cudaMemcpyAsync(d_y, ey, n * 2, cudaMemcpyHostToDevice, c->stream); }
+  unsigned long long cnt = 0;
+  if ((rc = fuse_reset_map(c, T)) == ESVO_OK && (rc = sgm_points(c, d_disp, d_x, d_y, n, map_T_world_frame_dev(c), f.pts, f.cnt)) == ESVO_OK) {
+    if (cudaMemcpyAsync(&cnt, f.cnt, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
+      rc = ESVO_ERR_CUDA;
+  }
+  cleanup();
+  if (rc) { c->win_pool.push_back(f); return rc; }
+  if (n_points) *n_points = (size_t)cnt;
+  if (cnt < min_points) {                                          // esvo_Mapping.cpp:481-483
+    c->win_pool.push_back(f);
+    if (accepted) *accepted = 0;
+    return ESVO_OK;
+  }
+  c->win.push_back(f);                                             // :485 dqvDepthPoints_.push_back(vdp_sgm)
+  std::memcpy(c->T_world_left, T, sizeof(c->T_world_left));
+  if ((rc = fuse_zero_fusion_counter(c))) return rc;
+  if ((rc = fuse_points(c, f.pts, (size_t)cnt, nullptr, 0, /*naive=*/1))) return rc;   // :486 naive_propagation
+  if ((rc = fuse_finish(c, true))) return rc;
+  if ((rc = map_count(c))) return rc;
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (accepted) *accepted = 1;
+  return ESVO_OK;
+}
+
+ESVO_API int esvo_window_download(esvo_ctx* c, int index, esvo_depth_point* out, size_t* n) {
+  CHECK_CTX(c);
+  if (!n || index < 0) return ESVO_ERR_INVALID_ARG;
+  { int rc0 = drain(c); if (rc0) return rc0; }
+  if ((size_t)index >= c->win.size()) { *n = 0; return ESVO_ERR_INVALID_ARG; }
+  const Ctx::WinFrame& f = c->win[(size_t)index];
+  unsigned long long cnt = 0;
+  ESVO_CUDA_TRY(c, cudaMemcpy(&cnt, f.cnt, 8, cudaMemcpyDeviceToHost));
+  if (cnt > *n) { *n = (size_t)cnt; return ESVO_ERR_CAPACITY; }
+  if (cnt && !out) return ESVO_ERR_INVALID_ARG;
+  if (cnt) ESVO_CUDA_TRY(c, cudaMemcpy(out, f.pts, (size_t)cnt * sizeof(esvo_depth_point), cudaMemcpyDeviceToHost));
+  *n = (size_t)cnt;
+  return ESVO_OK;
+}
+
 ESVO_API int esvo_mapping_reset(esvo_ctx* c) {
   CHECK_CTX(c);
   { int rc0 = drain(c); if (rc0) return rc0; }

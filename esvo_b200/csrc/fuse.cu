@@ -133,6 +133,8 @@ __global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, const double* __res
 }
 
 // ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
+// NAIVE = DepthFusion::naive_propagation (:232-288): same ordered replay, but nearest-wins instead of fusion.
+template <bool NAIVE>
 __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* head, const int32_t* __restrict__ next,
                                  unsigned long long seq_base, unsigned long long* scal) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,6 +174,18 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
       res = pres; age = P.age[sid];
       pc_rho = prho; pc_pending = true;
       fkey = seq_base + (unsigned long long)cid;
+      if (NAIVE) { s2 = 0; nu = 0; }               // dp_new.update(): the Gaussian fields only
+      return;
+    }
+    if (NAIVE) {                                   // case 2 of naive_propagation (:274-283)
+      if (rho > prho) return;                      // the propagated point is farther
+      if (pres < res) {                            // dm->get(row,col) = dp_prop
+        rho = prho; s2 = ps2; nu = pnu; var = pvar; res = pres; age = P.age[sid];
+        sdm = r.sd2;
+        x0 = P.x0[sid]; x1 = P.x1[sid]; pc0 = P.pc0[sid]; pc1 = P.pc1[sid]; pc2 = P.pc2[sid];
+        pc_pending = false;
+        erow = P.row[sid]; ecol = P.col[sid];
+      }
       return;
     }
     bool compat;
@@ -376,6 +390,108 @@ __global__ void __launch_bounds__(256) map_rank_permute_kernel(const esvo_depth_
   }
 }
 
+// ---- InitializationAtTime downstream of SGM (esvo_Mapping.cpp:446-480) + createEdgeMask (:1000-1044, undistorted
+// events, radius 0): one DepthPoint per event whose rectified pixel carries a valid, in-range disparity, kept in
+// event order (single-block ordered compaction, a few thousand events once at start-up).
+__device__ int block_excl_scan(int v, int* s_warp, int& total);
+// PerspectiveCamera::cam2World as the reference writes it (CameraSystem.cpp:120-139): invert [P; 0 0 0 z] and apply
+// it to (x, y, 1, 1).  The SGM points sit on exact integer pixels and are re-projected through T_frame_obs ~ I right
+// away, so floor(x) of the re-projection is decided by the last bit of p_cam: here (and only here) the device follows
+// the cofactor expansion operation by operation instead of using the closed form.
+__device__ bool inverse4_dev(const double* m, double* inv) {
+  double t[16];
+  t[0] = m[5]*m[10]*m[15] - m[5]*m[11]*m[14] - m[9]*m[6]*m[15] + m[9]*m[7]*m[14] + m[13]*m[6]*m[11] - m[13]*m[7]*m[10];
+  t[4] = -m[4]*m[10]*m[15] + m[4]*m[11]*m[14] + m[8]*m[6]*m[15] - m[8]*m[7]*m[14] - m[12]*m[6]*m[11] + m[12]*m[7]*m[10];
+  t[8] = m[4]*m[9]*m[15] - m[4]*m[11]*m[13] - m[8]*m[5]*m[15] + m[8]*m[7]*m[13] + m[12]*m[5]*m[11] - m[12]*m[7]*m[9];
+  t[12] = -m[4]*m[9]*m[14] + m[4]*m[10]*m[13] + m[8]*m[5]*m[14] - m[8]*m[6]*m[13] - m[12]*m[5]*m[10] + m[12]*m[6]*m[9];
+  t[1] = -m[1]*m[10]*m[15] + m[1]*m[11]*m[14] + m[9]*m[2]*m[15] - m[9]*m[3]*m[14] - m[13]*m[2]*m[11] + m[13]*m[3]*m[10];
+  t[5] = m[0]*m[10]*m[15] - m[0]*m[11]*m[14] - m[8]*m[2]*m[15] + m[8]*m[3]*m[14] + m[12]*m[2]*m[11] - m[12]*m[3]*m[10];
+  t[9] = -m[0]*m[9]*m[15] + m[0]*m[11]*m[13] + m[8]*m[1]*m[15] - m[8]*m[3]*m[13] - m[12]*m[1]*m[11] + m[12]*m[3]*m[9];
+  t[13] = m[0]*m[9]*m[14] - m[0]*m[10]*m[13] - m[8]*m[1]*m[14] + m[8]*m[2]*m[13] + m[12]*m[1]*m[10] - m[12]*m[2]*m[9];
+  t[2] = m[1]*m[6]*m[15] - m[1]*m[7]*m[14] - m[5]*m[2]*m[15] + m[5]*m[3]*m[14] + m[13]*m[2]*m[7] - m[13]*m[3]*m[6];
+  t[6] = -m[0]*m[6]*m[15] + m[0]*m[7]*m[14] + m[4]*m[2]*m[15] - m[4]*m[3]*m[14] - m[12]*m[2]*m[7] + m[12]*m[3]*m[6];
+  t[10] = m[0]*m[5]*m[15] - m[0]*m[7]*m[13] - m[4]*m[1]*m[15] + m[4]*m[3]*m[13] + m[12]*m[1]*m[7] - m[12]*m[3]*m[5];
+  t[14] = -m[0]*m[5]*m[14] + m[0]*m[6]*m[13] + m[4]*m[1]*m[14] - m[4]*m[2]*m[13] - m[12]*m[1]*m[6] + m[12]*m[2]*m[5];
+  t[3] = -m[1]*m[6]*m[11] + m[1]*m[7]*m[10] + m[5]*m[2]*m[11] - m[5]*m[3]*m[10] - m[9]*m[2]*m[7] + m[9]*m[3]*m[6];
+  t[7] = m[0]*m[6]*m[11] - m[0]*m[7]*m[10] - m[4]*m[2]*m[11] + m[4]*m[3]*m[10] + m[8]*m[2]*m[7] - m[8]*m[3]*m[6];
+  t[11] = -m[0]*m[5]*m[11] + m[0]*m[7]*m[9] + m[4]*m[1]*m[11] - m[4]*m[3]*m[9] - m[8]*m[1]*m[7] + m[8]*m[3]*m[5];
+  t[15] = m[0]*m[5]*m[10] - m[0]*m[6]*m[9] - m[4]*m[1]*m[10] + m[4]*m[2]*m[9] + m[8]*m[1]*m[6] - m[8]*m[2]*m[5];
+  double det = m[0]*t[0] + m[1]*t[4] + m[2]*t[8] + m[3]*t[12];
+  if (det == 0) return false;
+  det = 1.0 / det;
+  for (int i = 0; i < 16; ++i) inv[i] = t[i] * det;
+  return true;
+}
+__device__ void cam2world_general(const DevConsts& dc, double x, double y, double rho, double& p0, double& p1, double& p2) {
+  const double z = 1.0 / rho;
+  double Pt[16], Pi[16];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) Pt[q] = dc.Pl[q];
+  Pt[12] = 0; Pt[13] = 0; Pt[14] = 0; Pt[15] = z;
+  inverse4_dev(Pt, Pi);
+  const double xs[4] = {x, y, 1, 1};
+  double ps[4];
+  for (int i = 0; i < 4; ++i) {
+    double s = 0;
+    for (int k = 0; k < 4; ++k) s += (z * Pi[i * 4 + k]) * xs[k];
+    ps[i] = s;
+  }
+  p0 = ps[0] / ps[3]; p1 = ps[1] / ps[3]; p2 = ps[2] / ps[3];
+}
+__global__ void __launch_bounds__(1024) sgm_points_kernel(DevConsts dc, const int16_t* __restrict__ disp16,
+                                                          const uint16_t* __restrict__ ex, const uint16_t* __restrict__ ey, int n,
+                                                          const double* __restrict__ lut, const double* __restrict__ T_world_cam,
+                                                          double rho_min, double rho_max, long long age0, esvo_depth_point* out,
+                                                          unsigned long long* out_cnt) {
+  __shared__ int s_warp[33];
+  int running = 0;
+  for (int k0 = 0; k0 < n; k0 += blockDim.x) {
+    const int i = k0 + threadIdx.x;
+    int f = 0, xc = 0, yc = 0;
+    double rho = 0;
+    if (i < n && ex[i] < dc.W && ey[i] < dc.H) {
+      const size_t li = (size_t)ey[i] * dc.W + ex[i];
+      const double cx = lut[2 * li], cy = lut[2 * li + 1];
+      // floor()->int of a NaN / huge coordinate is UB in the reference; such events cannot be inside the image
+      if (cx > -1e9 && cx < 1e9 && cy > -1e9 && cy < 1e9) {
+        xc = (int)floor(cx); yc = (int)floor(cy);
+        if (xc >= 0 && xc < dc.W && yc >= 0 && yc < dc.H) {
+          const double disp = disp16[(size_t)yc * dc.W + xc] / 16.0;
+          rho = disp / (dc.Pl[0] * dc.baseline);
+          f = (!(disp < 0) && !(rho < rho_min || rho > rho_max)) ? 1 : 0;
+        }
+      }
+    }
+    int total;
+    const int pos = running + block_excl_scan(f, s_warp, total);
+    if (f) {
+      esvo_depth_point* o = out + pos;
+      o->row = xc; o->col = yc;                          // DepthPoint dp(x, y): the reference passes (x, y) as (row, col)
+      o->x[0] = xc * 1.0; o->x[1] = yc * 1.0;
+      double p0, p1, p2;
+      cam2world_general(dc, xc * 1.0, yc * 1.0, rho, p0, p1, p2);
+      o->p_cam[0] = p0; o->p_cam[1] = p1; o->p_cam[2] = p2;
+      o->inv_depth = rho;
+      { const double v = 0.001 * 0.001; o->variance = v < 1e-6 ? 1e-6 : v; }   // pow(0.001, 2), then boundVariance
+      o->scale2 = 0; o->nu = 0;                          // never initialised by the reference for these points
+      o->residual = 0.0; o->age = age0;
+      for (int q = 0; q < 16; ++q) o->T_world_cam[q] = T_world_cam[q];
+    }
+    running += total;
+  }
+  if (threadIdx.x == 0) *out_cnt = (unsigned long long)running;
+}
+// device copy of the current map's T_world_frame (uploaded by fuse_reset_map, stream-ordered)
+const double* map_T_world_frame_dev(Ctx* c) { return c->map->d_T_frame_world + 16; }
+int sgm_points(Ctx* c, const int16_t* d_disp, const uint16_t* d_ex, const uint16_t* d_ey, size_t n, const double* d_T_world_cam,
+               esvo_depth_point* out, unsigned long long* out_cnt) {
+  sgm_points_kernel<<<1, 1024, 0, c->stream>>>(c->dc, d_disp, d_ex, d_ey, (int)n, c->d_lut, d_T_world_cam, c->prm.invdepth_min_range,
+                                               c->prm.invdepth_max_range, (long long)c->prm.age_vis_threshold, out, out_cnt);
+  c->launches += 1;
+  ESVO_CUDA_TRY(c, cudaGetLastError());
+  return ESVO_OK;
+}
+
 __global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -459,7 +575,8 @@ int fuse_reset_map(Ctx* c, const double T[16]) {
 }
 
 // Stage one vector of DepthPoints (device array).  n_cap bounds the count when it lives on the device.
-int fuse_points(Ctx* c, const esvo_depth_point* d_pts, size_t n_cap, const uint64_t* d_n, int radius, int) {
+// naive != 0: naive_propagate_one_point (:290-327) -- the Gaussian propagation whatever LSnorm is.
+int fuse_points(Ctx* c, const esvo_depth_point* d_pts, size_t n_cap, const uint64_t* d_n, int radius, int naive) {
   MapState* ms = c->map;
   if (n_cap == 0) return ESVO_OK;
   if (ms->staged + n_cap > ms->prop_cap) {
@@ -470,7 +587,9 @@ int fuse_points(Ctx* c, const esvo_depth_point* d_pts, size_t n_cap, const uint6
   const int B = 128;
   FrameSet fs;
   fs.nframes = 1; fs.pts[0] = d_pts; fs.cnt[0] = (const unsigned long long*)d_n; fs.cap[0] = (int)n_cap; fs.off[0] = 0; fs.off[1] = (int)n_cap;
-  fuse_stage_kernel<<<div_up((int)n_cap, B), B, 0, c->stream>>>(c->dc, fs, ms->d_T_frame_world, radius, (int)ms->staged, ms->p,
+  DevConsts dcs = c->dc;
+  if (naive) dcs.lsnorm = ESVO_LSNORM_L2;
+  fuse_stage_kernel<<<div_up((int)n_cap, B), B, 0, c->stream>>>(dcs, fs, ms->d_T_frame_world, radius, (int)ms->staged, ms->p,
                                                                 ms->head, ms->next);
   c->launches += 1;
   ms->staged += n_cap;
@@ -501,11 +620,12 @@ int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
   return ESVO_OK;
 }
 
-int fuse_finish(Ctx* c) {
+int fuse_finish(Ctx* c, bool naive) {
   MapState* ms = c->map;
   if (ms->staged == 0) return ESVO_OK;
   const int npix = c->dc.W * c->dc.H, B = 128;
-  fuse_fold_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->seq_base, ms->d_scal);
+  if (naive) fuse_fold_kernel<true><<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->seq_base, ms->d_scal);
+  else fuse_fold_kernel<false><<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->seq_base, ms->d_scal);
   c->launches += 1;
   ms->seq_base += (unsigned long long)ms->staged * 9ULL;
   ms->staged = 0;

@@ -229,6 +229,22 @@ ESVO_API int esvo_mapping_at_time(esvo_ctx* ctx, const uint16_t* ex, const uint1
                                   const int64_t* et_ns, size_t n_events,
                                   const int64_t* pose_t_ns, const double* poses, size_t n_poses,
                                   uint64_t* counters_out);
+/* esvo_Mapping::InitializationAtTime (esvo_core/src/esvo_Mapping.cpp:433-492) downstream of its SGM call, incl.
+ * createEdgeMask (:1000-1044, undistorted events, radius 0) and DepthFusion::naive_propagation
+ * (esvo_core/src/core/DepthFusion.cpp:232-327).  `disp16` is the H*W CV_16S map cv::StereoSGBM::compute returns
+ * (disparity * 16, negative = invalid) for the current time-surface pair -- the SGM itself stays with the caller
+ * (OpenCV, once at start-up).  One DepthPoint (Gaussian, variance 1e-6, age = age_vis_threshold) is created per event
+ * whose rectified pixel carries a disparity inside the inverse-depth range, in event order; if there are at least
+ * `min_points` (INIT_SGM_DP_NUM_Threshold) of them they become the first vector of the fusion window and are splat
+ * (nearest wins) into a fresh map at T_world_left, which esvo_map_download then returns.  *accepted = 0 otherwise. */
+ESVO_API int esvo_init_from_disparity(esvo_ctx* ctx, const int16_t* disp16, const uint16_t* ex, const uint16_t* ey,
+                                      size_t n_events, const double T_world_left[16], size_t min_points,
+                                      size_t* n_points, int* accepted);
+
+/* Copies vector `index` (0 = oldest) of the fusion window dqvDepthPoints_ (esvo_Mapping.h:165) to the host, in its
+ * stored order; *n in: capacity, out: count.  ESVO_ERR_INVALID_ARG if there is no such vector. */
+ESVO_API int esvo_window_download(esvo_ctx* ctx, int index, esvo_depth_point* out, size_t* n);
+
 /* Drops the fusion window (dqvDepthPoints_) -- the reference does this on reset. */
 ESVO_API int esvo_mapping_reset(esvo_ctx* ctx);
 

@@ -269,6 +269,23 @@ inline void selectCloseEvents(std::vector<esvo::Event>& events_left /* time-orde
     --ev_end;
   }
 }
+//  * selectSGMEvents: the INITIALIZATION branch of dataTransferring (:538-552) -- window 2*BM_half_slice_thickness and
+//    `<=` instead of `<` on the count (one event more than PROCESS_EVENT_NUM).
+inline void selectSGMEvents(std::vector<esvo::Event>& events_left, int64_t t_end_ns, double BM_half_slice_thickness, size_t PROCESS_EVENT_NUM,
+                            std::vector<esvo::Event*>& vEventsPtr_left_SGM) {
+  vEventsPtr_left_SGM.clear();
+  if (events_left.empty()) return;
+  const int64_t t_begin_ns = fromSec(std::max(0.0, toSec(t_end_ns) - 2 * BM_half_slice_thickness));
+  auto lower = [&](int64_t t) {
+    size_t lo = 0, hi = events_left.size();
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (events_left[mid].ts < t) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  size_t ev_end = lower(t_end_ns);
+  const size_t ev_begin = lower(t_begin_ns);
+  if (ev_end == events_left.size()) return;   // the reference dereferences end() here (UB)
+  while (ev_end != ev_begin && vEventsPtr_left_SGM.size() <= PROCESS_EVENT_NUM) { vEventsPtr_left_SGM.push_back(&events_left[ev_end]); --ev_end; }
+}
 inline std::vector<int64_t> samplePoseStamps(int64_t t_end_ns, double BM_half_slice_thickness) {
   std::vector<int64_t> out;
   const double t_end = toSec(t_end_ns);
@@ -339,6 +356,22 @@ class esvo_Mapping {
       return false;
     if (out) *out = Counters{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]};
     return true;
+  }
+  // InitializationAtTime (esvo_Mapping.cpp:433-492).  The SGM stays where it is -- the node's
+  //   sgbm_->compute(TS_left, TS_right, dispMap)       (cv::StereoSGBM(0,48,11,968,3872,-1,0,11), esvo_Mapping.cpp:101-108,444)
+  // -- and its CV_16S result is passed in; everything downstream (edge mask AND disparity, DepthPoint creation,
+  // naive_propagation into the new DepthFrame, first window vector) runs on the device.  Returns false like the
+  // reference when fewer than INIT_SGM_DP_NUM_Threshold points survive.
+  bool InitializationAtTime(const esvo::StampedTimeSurfaceObs& TS_obs, const int16_t* dispMap16,
+                            const std::vector<esvo::Event*>& vEventsPtr_left_SGM, size_t INIT_SGM_DP_NUM_Threshold, size_t* n_points = nullptr) {
+    std::vector<uint16_t> ex, ey;
+    for (auto* e : vEventsPtr_left_SGM) { ex.push_back(e->x); ey.push_back(e->y); }
+    size_t n = 0; int accepted = 0;
+    if (esvo_init_from_disparity(cs_->ctx(), dispMap16, ex.data(), ey.data(), ex.size(), TS_obs.second.tr_.data(), INIT_SGM_DP_NUM_Threshold,
+                                 &n, &accepted) != ESVO_OK)
+      return false;
+    if (n_points) *n_points = n;
+    return accepted != 0;
   }
   void reset() { esvo_mapping_reset(cs_->ctx()); }
  private:

@@ -631,6 +631,77 @@ struct DepthFusion {
     }
     return numFusion;
   }
+  // naive_propagate_one_point (:290-327): always the Gaussian update, whatever LSnorm is
+  bool naive_propagate_one_point(const DepthPoint& prior, DepthPoint& prop, const Mat4& T) const {
+    double pp[3];
+    for (int i = 0; i < 3; ++i) pp[i] = T(i, 0) * prior.p_cam[0] + T(i, 1) * prior.p_cam[1] + T(i, 2) * prior.p_cam[2] + T(i, 3);
+    double xp[2];
+    cs->left.world2Cam(pp, xp);
+    if (!boundaryCheck(xp[0], xp[1], cs->left.W, cs->left.H)) return false;
+    prop = DepthPoint((int64_t)std::floor(xp[1]), (int64_t)std::floor(xp[0]));
+    prop.x[0] = xp[0]; prop.x[1] = xp[1];
+    double invDepth = 1.0 / pp[2];
+    double den = T(2, 0) * prior.p_cam[0] + T(2, 1) * prior.p_cam[1] + T(2, 3);
+    den /= prior.p_cam[2];
+    den += T(2, 2);
+    double J = T(2, 2) / (den * den);
+    prop.update(invDepth, J * J * prior.variance);
+    std::memcpy(prop.p_cam, pp, sizeof(pp));
+    prop.residual = prior.residual; prop.age = prior.age;
+    return true;
+  }
+  // naive_propagation (:232-288): nearest-wins z-buffer over the 2x2 neighbourhood, no fusion
+  void naive_propagation(const std::vector<DepthPoint>& obs, DepthMap& dm, const Mat4& T_world_frame) const {
+    Mat4 T_frame_world = rigid_inverse(T_world_frame);
+    for (const auto& o : obs) {
+      Mat4 T_frame_obs = mul(T_frame_world, o.T_world_cam);
+      DepthPoint prop;
+      if (!naive_propagate_one_point(o, prop, T_frame_obs)) continue;
+      for (int dy = 0; dy <= 1; ++dy)
+        for (int dx = 0; dx <= 1; ++dx) {
+          int row = (int)prop.row + dy, col = (int)prop.col + dx;
+          if (!boundaryCheck(col, row, cs->left.W, cs->left.H)) continue;
+          if (!dm.exists(row, col)) {                       // case 1
+            DepthPoint nw(row, col);
+            nw.update(prop.invDepth, prop.variance);
+            nw.residual = prop.residual; nw.age = prop.age;
+            cs->left.cam2World(nw.x, prop.invDepth, nw.p_cam);
+            dm.set(row, col, nw);
+          } else {                                           // case 2
+            DepthPoint& cur = dm.get(row, col);
+            if (cur.invDepth > prop.invDepth) continue;      // the propagated point is farther
+            if (prop.residual < cur.residual) cur = prop;    // (copies row_/col_/x_ too)
+          }
+        }
+    }
+  }
+  // The part of esvo_Mapping::InitializationAtTime after the SGM call (esvo_Mapping.cpp:446-480) with
+  // createEdgeMask(..., bUndistortEvents = true, radius = 0) (:1000-1044) inlined: one DepthPoint per event whose
+  // rectified pixel carries a valid disparity in range.  disp16 = CV_16S fixed point (disparity * 16).
+  void sgm_points(const int16_t* disp16, const uint16_t* ex, const uint16_t* ey, size_t n, const Mat4& T_world_cam, double rho_min,
+                  double rho_max, double age0, std::vector<DepthPoint>& out) const {
+    out.clear();
+    const int W = cs->left.W, H = cs->left.H;
+    const double var_SGM = std::pow(0.001, 2);
+    for (size_t i = 0; i < n; ++i) {
+      if (ex[i] >= W || ey[i] >= H) continue;
+      const double* coor = &cs->left.lut[2 * ((size_t)ey[i] * W + ex[i])];     // getRectifiedUndistortedCoordinate
+      const int xc = (int)std::floor(coor[0]), yc = (int)std::floor(coor[1]);
+      if (xc < 0 || xc >= W || yc < 0 || yc >= H) continue;
+      const double disp = disp16[(size_t)yc * W + xc] / 16.0;
+      if (disp < 0) continue;
+      DepthPoint dp(xc, yc);                                   // DepthPoint dp(x, y): the reference passes (x, y) as (row, col)
+      dp.x[0] = xc * 1.0; dp.x[1] = yc * 1.0;
+      const double invDepth = disp / (cs->left.P[0] * cs->baseline);
+      if (invDepth < rho_min || invDepth > rho_max) continue;
+      cs->left.cam2World(dp.x, invDepth, dp.p_cam);
+      dp.update(invDepth, var_SGM);
+      dp.residual = 0.0;
+      dp.age = (int64_t)age0;
+      dp.T_world_cam = T_world_cam;
+      out.push_back(dp);
+    }
+  }
   // update (:71-87)
   int update(const std::vector<DepthPoint>& obs, DepthMap& dm, const Mat4& T_world_frame, int radius) const {
     int numFusion = 0;

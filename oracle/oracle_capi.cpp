@@ -186,6 +186,30 @@ OAPI int esvo_oracle_map_download(esvo_oracle_ctx* c, esvo_depth_point* out, siz
   *n = cnt;
   return ESVO_OK;
 }
+// InitializationAtTime (esvo_Mapping.cpp:433-492) downstream of the SGM call (the disparity map is an input).
+OAPI int esvo_oracle_init_from_disparity(esvo_oracle_ctx* c, const int16_t* disp16, const uint16_t* ex, const uint16_t* ey, size_t n,
+                                         const double T[16], size_t min_points, size_t* n_points, int* accepted) {
+  if (!c || !disp16 || !T || (n && (!ex || !ey))) return ESVO_ERR_INVALID_ARG;
+  c->dmap.reset(c->cs.left.W, c->cs.left.H);
+  c->T_world_frame = Mat4::from(T);
+  std::vector<DepthPoint> vdp;
+  c->fusor.sgm_points(disp16, ex, ey, n, c->T_world_frame, c->prm.invdepth_min_range, c->prm.invdepth_max_range,
+                      (double)c->prm.age_vis_threshold, vdp);
+  if (n_points) *n_points = vdp.size();
+  if (vdp.size() < min_points) { if (accepted) *accepted = 0; return ESVO_OK; }   // :481-483
+  c->window.push_back(vdp);                                                        // :485
+  c->fusor.naive_propagation(vdp, c->dmap, c->T_world_frame);                      // :486
+  if (accepted) *accepted = 1;
+  return ESVO_OK;
+}
+OAPI int esvo_oracle_window_download(esvo_oracle_ctx* c, int index, esvo_depth_point* out, size_t* n) {
+  if (!c || !n || index < 0 || (size_t)index >= c->window.size()) return ESVO_ERR_INVALID_ARG;
+  const auto& v = c->window[(size_t)index];
+  if (v.size() > *n) { *n = v.size(); return ESVO_ERR_CAPACITY; }
+  for (size_t i = 0; i < v.size(); ++i) to_pod(v[i], out + i);
+  *n = v.size();
+  return ESVO_OK;
+}
 OAPI int esvo_oracle_set_exec_threads(esvo_oracle_ctx* c, int n) { c->exec_threads = n < 1 ? 1 : n; return ESVO_OK; }
 OAPI int esvo_oracle_mapping_reset(esvo_oracle_ctx* c) { c->window.clear(); return ESVO_OK; }
 

@@ -204,6 +204,58 @@ def test_mapping_at_time_multi_frame(oracle_lib, product_lib, rig):
         assert (r < 1e-4).mean() > 0.995 and np.median(r) < 1e-7
 
 
+def test_initialization_from_sgm_disparity(oracle_lib, product_lib):
+    """InitializationAtTime (esvo_Mapping.cpp:433-492): the node's own cv::StereoSGBM(0,48,11,968,3872,-1,0,11) on the TS pair,
+    then edge mask AND disparity -> Gaussian DepthPoints -> naive_propagation; the following MappingAtTime frame fuses a
+    window that contains the SGM vector."""
+    import cv2
+    s = scenario("hkust")
+    o, g = make_backends("hkust", oracle_lib, product_lib)
+    tl, tr = build_ts_pair(o, s)
+    build_ts_pair(g, s)
+    H, W = 260, 346
+    sgbm = cv2.StereoSGBM_create(0, 48, 11, 8 * 11 * 11, 32 * 11 * 11, -1, 0, 11)
+    disp = sgbm.compute(np.asarray(tl).reshape(H, W), np.asarray(tr).reshape(H, W))
+    assert disp.dtype == np.int16 and (disp >= 0).mean() > 0.05
+    sd = s["seeds"]
+    T = s["T_world_left"]
+    res = [be.init_from_disparity(disp, sd["x"], sd["y"], T, min_points=50) for be in (o, g)]
+    assert res[0] == res[1] and res[0][1] and res[0][0] >= 50, res
+    mo, mg = o.map_download(), g.map_download()
+    assert mo.size == mg.size and mo.size > res[0][0]
+    for f in ("row", "col", "age"):
+        assert np.array_equal(mo[f], mg[f]), f
+    for f in ("inv_depth", "variance", "residual", "x"):
+        assert np.allclose(mo[f], mg[f], rtol=1e-13, atol=0), f
+    assert np.allclose(mo["p_cam"], mg["p_cam"], rtol=1e-9, atol=1e-12)   # closed-form cam2World in the fold (DESIGN.md deviation 3)
+    # the SGM vector itself (first vector of the window), element by element
+    wo, wg = o.window_download(0), g.window_download(0)
+    assert wo.size == wg.size == res[0][0]
+    for f in wo.dtype.names:
+        assert np.array_equal(wo[f], wg[f]), f                            # bit-exact incl. p_cam (same cofactor inverse)
+    # too few points -> rejected, nothing pushed to the window
+    r2 = [be.init_from_disparity(disp, sd["x"][:3], sd["y"][:3], T, min_points=50) for be in (o, g)]
+    assert r2[0] == r2[1] and not r2[0][1]
+    # re-initialise, then a regular mapping frame on top of the SGM vector
+    for be in (o, g):
+        be.mapping_reset()
+        be.init_from_disparity(disp, sd["x"], sd["y"], T, min_points=50)
+        be.set_ts_pair(tl, tr, T)
+    co = o.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+    cg = g.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+    assert co["n_seeds"] == cg["n_seeds"] and co["n_culled"] == cg["n_culled"] and co["map_size"] == cg["map_size"]
+    assert co["n_fusions"] == cg["n_fusions"]
+    mo, mg = o.map_download(), g.map_download()
+    assert np.array_equal(mo["row"], mg["row"]) and np.array_equal(mo["col"], mg["col"])
+    # The SGM points carry no Student-t scale / nu (the reference never initialises them: DepthPoint.cpp:7-35, UB there;
+    # zero here and in the oracle), so pixels they fuse into turn NaN on both sides: compare NaN patterns, then values.
+    a, b = mo["inv_depth"], mg["inv_depth"]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    fin = ~np.isnan(a)
+    r = rel(b[fin], a[fin])
+    assert fin.sum() > 500 and (r < 1e-4).mean() > 0.995 and np.median(r) < 1e-7
+
+
 def _tracking_case(oracle_lib, product_lib, rig, analytical, perturb=True, seed=11):
     s = scenario(rig)
     o, g = make_backends(rig, oracle_lib, product_lib)

@@ -179,3 +179,37 @@ def test_oracle_forward_time_surface_against_numpy(oracle_lib):
     img = np.asarray(img).reshape(H, W)
     assert (img == 255).sum() > 100                           # the clamp is exercised
     assert np.abs(ref.astype(int) - img.astype(int)).max() <= 1 and (ref != img).mean() < 1e-3
+
+
+def test_oracle_init_from_disparity_kat(oracle_lib):
+    """InitializationAtTime after SGM (esvo_Mapping.cpp:446-486): rho = disp / (P00 * baseline); events on pixels with
+    invalid or out-of-range disparity are dropped; naive_propagation keeps the NEAREST point per pixel."""
+    l, r = configs.rig_calibs("hkust")
+    p = configs.params_for("hkust", oracle_lib)
+    o = capi.Backend(oracle_lib, l, r, p)
+    W, H = 346, 260
+    fb = o.get_derived()["baseline"] * 189.705
+    disp = np.full((H, W), -16, np.int16)                 # invalid everywhere ...
+    disp[100:140, 100:200] = 16 * 10                      # ... except a block at 10 px  -> rho = 10 / fb
+    disp[120:125, 150:160] = 16 * 20                      # and a nearer patch at 20 px
+    disp[10:20, 10:20] = 16 * 1                           # rho below invDepth_min_range (0.25): 1 / 13.86 = 0.072 -> dropped
+    _, _, lut, _ = o.get_rectify_tables(0)
+    lut = np.asarray(lut).reshape(H, W, 2)
+    ys, xs = np.mgrid[90:150:3, 90:210:3]
+    ex = xs.ravel().astype(np.uint16); ey = ys.ravel().astype(np.uint16)
+    T = np.eye(4)
+    n, acc = o.init_from_disparity(disp, ex, ey, T, min_points=10)
+    # expectation from the LUT
+    cx = np.floor(lut[ey, ex, 0]).astype(int); cy = np.floor(lut[ey, ex, 1]).astype(int)
+    inside = (cx >= 0) & (cx < W) & (cy >= 0) & (cy < H)
+    d = np.where(inside, disp[np.clip(cy, 0, H - 1), np.clip(cx, 0, W - 1)], -16) / 16.0
+    rho = d / fb
+    keep = inside & (d >= 0) & (rho >= 0.25) & (rho <= 2.0)
+    assert acc and n == keep.sum() and n > 100
+    m = o.map_download()
+    assert m.size > n                                      # 2x2 splats
+    got = {(int(e["row"]), int(e["col"])): float(e["inv_depth"]) for e in m}
+    assert set(np.round(list(got.values()), 12)) <= set(np.round(np.unique(rho[keep]), 12))
+    assert abs(max(got.values()) - 20 / fb) < 1e-12 and abs(min(got.values()) - 10 / fb) < 1e-12
+    n2, acc2 = o.init_from_disparity(disp, ex[:5], ey[:5], T, min_points=10)
+    assert not acc2 and n2 <= 5
