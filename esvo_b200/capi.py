@@ -373,6 +373,9 @@ class Backend:
                    C.byref(n), C.byref(acc))
         return int(n.value), bool(acc.value)
 
+    def ts_set_unordered_input(self, cam, enable):
+        self._call("ts_set_unordered_input", [C.c_int, C.c_int], int(cam), int(bool(enable)))
+
     def window_download(self, index):
         out = np.zeros(self.W * self.H, DEPTH_POINT_DTYPE)
         n = C.c_size_t(out.size)

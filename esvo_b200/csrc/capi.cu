@@ -383,6 +383,12 @@ ESVO_API int esvo_ts_build(esvo_ctx* c, int cam, int64_t T, int64_t* idx_out, ui
   if (flags[1]) { c->set_error("events were not pushed in time order (unsupported on the device path)"); return ESVO_ERR_UNSUPPORTED; }
   return ESVO_OK;
 }
+ESVO_API int esvo_ts_set_unordered_input(esvo_ctx* c, int cam, int enable) {
+  CHECK_CTX(c);
+  if (cam < 0 || cam > 1) return ESVO_ERR_INVALID_ARG;
+  c->ts[cam].unordered = enable != 0;
+  return ESVO_OK;
+}
 ESVO_API int esvo_ts_reset(esvo_ctx* c, int cam) {
   CHECK_CTX(c);
   if (cam < 0 || cam > 1) return ESVO_ERR_INVALID_ARG;

@@ -64,6 +64,78 @@ __global__ void ts_scatter_fix_kernel(const uint16_t* __restrict__ ex, const uin
   if (idx_grid[p] == gbase + (long long)i) { t_grid[p] = et[i]; pol_grid[p] = ep[i]; }
 }
 
+// ---- opt-in: stamps out of order.  The reference's eventsCallback (TimeSurface.cpp:403-425) insertion-sorts the new
+// event into its global deque and then queues events_.back(), i.e. the event with the LARGEST stamp seen so far (the
+// most recent arrival among equal stamps) -- for ordered input that is the new event itself.  So arrival i queues the
+// running arg-max of (stamp, arrival) over everything pushed so far: a prefix scan with the associative, non-commutative
+// operator  a (+) b = (b.t >= a.t ? b : a).  The effective events are written to the log in arrival order; their stamps
+// are non-decreasing, so everything downstream (split by T, queue-length rule, eviction) is unchanged.
+struct RunMax { long long t; int i; };
+__device__ __forceinline__ RunMax runmax_op(const RunMax& a, const RunMax& b) { return b.t >= a.t ? b : a; }
+// (1) per block of 1024 arrivals: inclusive scan -> raw_eff[i] = batch index of the running maximum inside the block;
+//     block aggregate -> agg[b] (stamp), agg[nb + b] (batch index)
+__global__ void __launch_bounds__(1024) ts_runmax_block_kernel(const int64_t* __restrict__ t, int n, int32_t* __restrict__ eff,
+                                                               long long* __restrict__ agg, int nb) {
+  __shared__ long long s_t[32];
+  __shared__ int s_i[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  RunMax v{i < n ? (long long)t[i] : (long long)0x8000000000000000LL, i < n ? i : -1};
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    RunMax u{__shfl_up_sync(0xffffffffu, v.t, o), __shfl_up_sync(0xffffffffu, v.i, o)};
+    if (lane >= o) v = runmax_op(u, v);
+  }
+  if (lane == 31) { s_t[w] = v.t; s_i[w] = v.i; }
+  __syncthreads();
+  if (w == 0) {
+    RunMax a{s_t[lane], s_i[lane]};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      RunMax u{__shfl_up_sync(0xffffffffu, a.t, o), __shfl_up_sync(0xffffffffu, a.i, o)};
+      if (lane >= o) a = runmax_op(u, a);
+    }
+    s_t[lane] = a.t; s_i[lane] = a.i;
+  }
+  __syncthreads();
+  if (w > 0) { RunMax pre{s_t[w - 1], s_i[w - 1]}; v = runmax_op(pre, v); }
+  if (i < n) eff[i] = v.i;
+  if (threadIdx.x == 1023) { agg[blockIdx.x] = v.t; agg[nb + blockIdx.x] = v.i; }
+}
+// (2) one thread: exclusive scan of the block aggregates seeded with the carried back() event; agg[2nb + b] = stamp and
+//     agg[3nb + b] = batch index (-1 = the carried event) of the prefix of block b; back <- new maximum (old one kept)
+__global__ void ts_runmax_carry_kernel(long long* agg, int nb, const uint16_t* __restrict__ x, const uint16_t* __restrict__ y,
+                                       const int64_t* __restrict__ t, const uint8_t* __restrict__ p, long long* back) {
+  if (threadIdx.x || blockIdx.x) return;
+  for (int q = 0; q < 5; ++q) back[5 + q] = back[q];
+  RunMax run{back[4] ? back[0] : (long long)0x8000000000000000LL, -1};
+  for (int b = 0; b < nb; ++b) {
+    agg[2 * nb + b] = run.t; agg[3 * nb + b] = run.i;
+    run = runmax_op(run, RunMax{agg[b], (int)agg[nb + b]});
+  }
+  if (run.i >= 0) { back[0] = t[run.i]; back[1] = x[run.i]; back[2] = y[run.i]; back[3] = p ? p[run.i] : 1; back[4] = 1; }
+}
+// (3) write the effective events to the log and scatter them (same as ts_ingest_kernel on ordered input)
+__global__ void ts_effective_kernel(const uint16_t* __restrict__ sx, const uint16_t* __restrict__ sy, const int64_t* __restrict__ st,
+                                    const uint8_t* __restrict__ sp, int n, const int32_t* __restrict__ eff,
+                                    const long long* __restrict__ agg, int nb, const long long* __restrict__ back,
+                                    uint16_t* __restrict__ ex, uint16_t* __restrict__ ey, int64_t* __restrict__ et, uint8_t* __restrict__ ep,
+                                    long long gbase, int W, int H, long long* __restrict__ idx_grid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = i >> 10;
+  int j = eff[i];
+  const long long pre_t = agg[2 * nb + b];
+  const int pre_i = (int)agg[3 * nb + b];
+  const bool have_pre = pre_i >= 0 || back[5 + 4] != 0;
+  if (have_pre && !((long long)st[j] >= pre_t)) j = pre_i;    // the prefix (earlier arrivals) holds a strictly later stamp
+  int x, y; long long t; int pol;
+  if (j >= 0) { x = sx[j]; y = sy[j]; t = st[j]; pol = sp ? sp[j] : 1; }
+  else { t = back[5]; x = (int)back[6]; y = (int)back[7]; pol = (int)back[8]; }   // the event carried over from earlier pushes
+  ex[i] = (uint16_t)x; ey[i] = (uint16_t)y; et[i] = t; ep[i] = (uint8_t)pol;
+  if (x >= W || y >= H) return;
+  atomicMax(&idx_grid[(size_t)y * W + x], gbase + (long long)i);
+}
+
 // ---- build, step 0: split position k = first log entry with t >= T; flag the general path ----
 __global__ void ts_split_kernel(const int64_t* __restrict__ et, size_t n, long long T, int32_t* scalars) {
   size_t lo = 0, hi = n;
@@ -294,6 +366,7 @@ int ts_reset_state(Ctx* c, int cam) {
   long long mn = INT64_MIN;
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.max_t, &mn, 8, cudaMemcpyHostToDevice, c->stream));
   ESVO_CUDA_TRY(c, cudaMemsetAsync(s.img_out, 0, (size_t)c->dc.pitch * c->dc.H, c->stream));
+  if (s.back) ESVO_CUDA_TRY(c, cudaMemsetAsync(s.back, 0, 80, c->stream));
   ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   s.log_n = 0; s.log_base = 0; s.built = false; s.last_img = s.img_out;
   return ESVO_OK;
@@ -324,7 +397,7 @@ void ts_free(Ctx* c, int cam) {
   TsState& s = c->ts[cam];
   void* ps[] = {s.ex2, s.ey2, s.et2, s.ep2, s.ex, s.ey, s.et, s.ep, s.cur_idx, s.cur_t, s.cur_pol, s.base_idx, s.base_t, s.base_pol, s.tmp_idx,
                 s.tmp_t, s.tmp_pol, s.cnt, s.out_idx, s.img_med, s.img_out, s.map1, s.map2, s.scalars, s.max_t,
-                s.fwd_lut, s.fwd_head, s.fwd_next, s.fwd_val};
+                s.fwd_lut, s.fwd_head, s.fwd_next, s.fwd_val, s.raw_x, s.raw_y, s.raw_t, s.raw_p, s.raw_eff, s.agg, s.back};
   for (void* p : ps) if (p) cudaFree(p);
   s = TsState();
 }
@@ -366,7 +439,37 @@ int ts_push(Ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t
   const int B = 256;
   unsigned g = (unsigned)((n + B - 1) / B);
   long long gbase = s.log_base + (long long)off;
-  if (dev_src) {
+  if (s.unordered) {
+    const int nb = (int)((n + 1023) / 1024);
+    if (!s.back) { ESVO_CUDA_TRY(c, dmalloc(&s.back, 10)); ESVO_CUDA_TRY(c, cudaMemsetAsync(s.back, 0, 80, c->stream)); }
+    if (n > s.raw_cap) {
+      ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      void* olds[] = {s.raw_x, s.raw_y, s.raw_t, s.raw_p, s.raw_eff};
+      for (void* q : olds) if (q) cudaFree(q);
+      s.raw_cap = std::max<size_t>(n, 1 << 16);
+      ESVO_CUDA_TRY(c, dmalloc(&s.raw_x, s.raw_cap)); ESVO_CUDA_TRY(c, dmalloc(&s.raw_y, s.raw_cap)); ESVO_CUDA_TRY(c, dmalloc(&s.raw_t, s.raw_cap));
+      ESVO_CUDA_TRY(c, dmalloc(&s.raw_p, s.raw_cap)); ESVO_CUDA_TRY(c, dmalloc(&s.raw_eff, s.raw_cap));
+    }
+    if ((size_t)nb * 4 > s.agg_cap) {
+      ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      if (s.agg) cudaFree(s.agg);
+      s.agg_cap = std::max<size_t>((size_t)nb * 4, 1024);
+      ESVO_CUDA_TRY(c, dmalloc(&s.agg, s.agg_cap));
+    }
+    const uint16_t *sx = x, *sy = y; const int64_t* st = t; const uint8_t* sp = p;
+    if (!dev_src) {
+      ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.raw_x, x, n * 2, cudaMemcpyHostToDevice, c->stream));
+      ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.raw_y, y, n * 2, cudaMemcpyHostToDevice, c->stream));
+      ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.raw_t, t, n * 8, cudaMemcpyHostToDevice, c->stream));
+      if (p) ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.raw_p, p, n, cudaMemcpyHostToDevice, c->stream));
+      sx = s.raw_x; sy = s.raw_y; st = s.raw_t; sp = p ? s.raw_p : nullptr;
+    }
+    ts_runmax_block_kernel<<<nb, 1024, 0, c->stream>>>(st, (int)n, s.raw_eff, (long long*)s.agg, nb);
+    ts_runmax_carry_kernel<<<1, 32, 0, c->stream>>>((long long*)s.agg, nb, sx, sy, st, sp, (long long*)s.back);
+    ts_effective_kernel<<<g, B, 0, c->stream>>>(sx, sy, st, sp, (int)n, s.raw_eff, (const long long*)s.agg, nb, (const long long*)s.back,
+                                                s.ex + off, s.ey + off, s.et + off, s.ep + off, gbase, c->dc.W, c->dc.H, (long long*)s.cur_idx);
+    c->launches += 3;
+  } else if (dev_src) {
     ts_ingest_kernel<<<g, B, 0, c->stream>>>(x, y, t, p, n, s.ex + off, s.ey + off, s.et + off, s.ep + off, gbase, c->dc.W, c->dc.H,
                                              (long long*)s.cur_idx, s.scalars, (const long long*)s.max_t);
   } else {

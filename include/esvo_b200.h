@@ -177,6 +177,14 @@ ESVO_API int esvo_get_derived(esvo_ctx* ctx, double out[4]);
  * (TimeSurface.cpp:403-425, TimeSurface.h:39-50).  cam: 0 left, 1 right. */
 ESVO_API int esvo_ts_push_events(esvo_ctx* ctx, int cam, const uint16_t* x, const uint16_t* y,
                                  const int64_t* t_ns, const uint8_t* pol, size_t n);
+/* Out-of-order stamps.  The reference's eventsCallback insertion-sorts every new event into its global deque and then
+ * queues events_.back() -- the event with the largest stamp so far -- into the per-pixel queues
+ * (esvo_time_surface/src/TimeSurface.cpp:410-422); for time-ordered input that is the new event itself.  With
+ * enable = 1 pushes of this camera go through a device prefix scan (running arg-max of the stamps) that reproduces
+ * this for arbitrary input order, at the cost of two extra kernels per push.  With enable = 0 (default) input must be
+ * time-ordered; a violation is detected on the device and reported by esvo_ts_build as ESVO_ERR_UNSUPPORTED. */
+ESVO_API int esvo_ts_set_unordered_input(esvo_ctx* ctx, int cam, int enable);
+
 /* replaces: TimeSurface::createTimeSurfaceAtTime (TimeSurface.cpp:52-152) incl.
  * EventQueueMat::getMostRecentEventBeforeT (TimeSurface.h:52-75).
  * idx_grid_out (H*W, may be NULL): index, in push order since create/reset, of the event each

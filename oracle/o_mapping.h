@@ -43,6 +43,7 @@ struct TimeSurface {
     if (last.x >= W || last.y >= H) return;
     auto& q = eq[(size_t)last.x + (size_t)W * last.y];
     q.push_back(last);
+    q.back().idx = e.idx;   // the index grid reports the ARRIVAL that queued the entry (== last.idx for time-ordered input)
     while (q.size() > queueLen) q.pop_front();
   }
   // getMostRecentEventBeforeT (TimeSurface.h:52-75)

@@ -202,6 +202,7 @@ OAPI int esvo_oracle_init_from_disparity(esvo_oracle_ctx* c, const int16_t* disp
   if (accepted) *accepted = 1;
   return ESVO_OK;
 }
+OAPI int esvo_oracle_ts_set_unordered_input(esvo_oracle_ctx*, int, int) { return ESVO_OK; }   // the literal port always handles it
 OAPI int esvo_oracle_window_download(esvo_oracle_ctx* c, int index, esvo_depth_point* out, size_t* n) {
   if (!c || !n || index < 0 || (size_t)index >= c->window.size()) return ESVO_ERR_INVALID_ARG;
   const auto& v = c->window[(size_t)index];

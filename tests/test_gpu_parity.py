@@ -80,6 +80,37 @@ def test_time_surface_forward_mode_bit_exact(oracle_lib, product_lib, rig, media
     assert (to == 255).any()
 
 
+def test_time_surface_unordered_stamps(oracle_lib, product_lib):
+    """Out-of-order stamps with esvo_ts_set_unordered_input: the device prefix scan (running arg-max of the stamps,
+    carried across pushes) reproduces the reference's events_.back() behaviour bit for bit; without the switch the
+    violation is reported."""
+    s = scenario("hkust")
+    o, g = make_backends("hkust", oracle_lib, product_lib)
+    e = s["left"]
+    rng = np.random.default_rng(9)
+    t = e["t"].copy()
+    late = rng.random(t.size) < 0.08                       # 8 % of the events arrive with a stamp up to 2 ms in the past
+    t[late] -= rng.integers(1_000, 2_000_000, late.sum())
+    t[0] = e["t"][0]
+    assert (np.diff(t) < 0).sum() > 100
+    g.ts_set_unordered_input(0, True)
+    n = t.size
+    cuts = [0, 700, 701, 1024, 5000, n // 2, n]              # batch boundaries inside / across scan blocks
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        for be in (o, g):
+            be.ts_push_events(0, e["x"][a:b], e["y"][a:b], t[a:b], e["p"][a:b])
+    for T in (int(t.max()) + 1, int(np.sort(t)[n // 2]), int(np.sort(t)[n - 100])):
+        io, to = o.ts_build(0, T)
+        ig, tg = g.ts_build(0, T)
+        assert np.array_equal(io, ig), f"idx grid differs T={T}: {(io != ig).sum()} px"
+        assert np.array_equal(to, tg)
+    # default mode: the same input is rejected, not silently mis-handled
+    g.ts_set_unordered_input(1, False)
+    g.ts_push_events(1, e["x"][:5000], e["y"][:5000], t[:5000], e["p"][:5000])
+    with pytest.raises(capi.EsvoError):
+        g.ts_build(1, int(t.max()) + 1)
+
+
 def _bm_pair(oracle_lib, product_lib, rig, tweak=None):
     s = scenario(rig)
     o, g = make_backends(rig, oracle_lib, product_lib, tweak=tweak)

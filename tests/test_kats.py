@@ -213,3 +213,20 @@ def test_oracle_init_from_disparity_kat(oracle_lib):
     assert abs(max(got.values()) - 20 / fb) < 1e-12 and abs(min(got.values()) - 10 / fb) < 1e-12
     n2, acc2 = o.init_from_disparity(disp, ex[:5], ey[:5], T, min_points=10)
     assert not acc2 and n2 <= 5
+
+
+def test_oracle_unordered_stamps_quirk(oracle_lib):
+    """eventsCallback (TimeSurface.cpp:410-422) queues events_.back() -- the latest STAMP so far -- not the new event:
+    an event that arrives with an older stamp re-queues the current latest event at ITS pixel instead."""
+    l, r = configs.rig_calibs("hkust")
+    o = capi.Backend(oracle_lib, l, r, configs.params_for("hkust", oracle_lib))
+    x = np.array([10, 20, 30, 40], np.uint16); y = np.array([5, 5, 5, 5], np.uint16)
+    t = np.array([10, 30, 20, 40], np.int64) + 1_000_000_000; p = np.ones(4, np.uint8)
+    o.ts_push_events(0, x, y, t, p)
+    idx, _ = o.ts_build(0, int(t.max()) + 1)
+    idx = np.asarray(idx).reshape(260, 346)
+    assert idx[5, 10] == 0 and idx[5, 20] == 2 and idx[5, 30] == -1 and idx[5, 40] == 3
+    # T between the stamps: the entry queued by arrival 2 carries stamp 30
+    idx2, _ = o.ts_build(0, 1_000_000_025)
+    idx2 = np.asarray(idx2).reshape(260, 346)
+    assert idx2[5, 10] == 0 and idx2[5, 20] == -1 and idx2[5, 40] == -1
