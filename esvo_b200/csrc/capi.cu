@@ -201,11 +201,10 @@ ESVO_API int esvo_set_pipeline_depth(esvo_ctx* c, int depth) {
     // The time-surface chain of a frame is ~8 short dependent kernels per camera; with the SMs saturated by the
     // LM kernels of the frames in flight, each of them would queue behind pending LM blocks.  The two cameras get
     // their own streams, at the highest priority: their blocks are placed as soon as any LM block retires.
-    static const bool prio = [] { const char* e = getenv("ESVO_TS_PRIO"); return e ? atoi(e) != 0 : true; }();
     int lo = 0, hi = 0;
     ESVO_CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
     for (int k = 0; k < 2; ++k)
-      if (c->s_tsc[k] == c->s_main) ESVO_CUDA_TRY(c, cudaStreamCreateWithPriority(&c->s_tsc[k], cudaStreamNonBlocking, prio ? hi : lo));
+      if (c->s_tsc[k] == c->s_main) ESVO_CUDA_TRY(c, cudaStreamCreateWithPriority(&c->s_tsc[k], cudaStreamNonBlocking, hi));
     if (!c->ev_ts_join) ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ts_join, cudaEventDisableTiming));
     for (int i = 1; i < depth; ++i) if ((rc = slot_alloc(c, i))) return rc;
   } else {

@@ -219,8 +219,10 @@ ESVO_API int esvo_init_from_disparity(esvo_ctx* c, const int16_t* disp16, const 
   if (rc) return rc;
   auto cleanup = [&]() { cudaFree(d_disp); cudaFree(d_x); cudaFree(d_y); };
   if (dmalloc(&d_disp, npix) || dmalloc(&d_x, n) || dmalloc(&d_y, n)) { cleanup(); c->win_pool.push_back(f); return ESVO_ERR_CUDA; }
-  cudaMemcpyAsync(d_disp, disp16, npix * 2, cudaMemcpyHostToDevice, c->stream);
-  if (n) { cudaMemcpyAsync(d_x, ex, n * 2, cudaMemcpyHostToDevice, c->stream); cudaMemcpyAsync(d_y, ey, n * 2, cudaMemcpyHostToDevice, c->stream); }
+  cudaError_t ce = cudaMemcpyAsync(d_disp, disp16, npix * 2, cudaMemcpyHostToDevice, c->stream);
+  if (n && ce == cudaSuccess) ce = cudaMemcpyAsync(d_x, ex, n * 2, cudaMemcpyHostToDevice, c->stream);
+  if (n && ce == cudaSuccess) ce = cudaMemcpyAsync(d_y, ey, n * 2, cudaMemcpyHostToDevice, c->stream);
+  if (ce != cudaSuccess) { cleanup(); c->win_pool.push_back(f); c->set_error(cudaGetErrorString(ce)); return ESVO_ERR_CUDA; }
   unsigned long long cnt = 0;
   if ((rc = fuse_reset_map(c, T)) == ESVO_OK && (rc = sgm_points(c, d_disp, d_x, d_y, n, map_T_world_frame_dev(c), f.pts, f.cnt)) == ESVO_OK) {
     if (cudaMemcpyAsync(&cnt, f.cnt, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)

@@ -1,5 +1,6 @@
 #!/bin/bash
-# usage: sweep_env.sh VAR "v1 v2 ..." [repeats] -- runs bench.py (no CPU baseline) per value, prints resident / e2e ms per step
+# usage: sweep_env.sh VAR "v1 v2 ..." [repeats] -- runs bench.py (no CPU baseline) once per value of an environment
+# variable (e.g. ESVO_BENCH_SAMPLER "nvml smi"), prints resident / e2e ms per step and host issue statistics
 VAR=$1; VALS=$2; REP=${3:-1}
 for v in $VALS; do for r in $(seq $REP); do
   env $VAR=$v timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
