@@ -142,3 +142,37 @@ def test_mapping_tracking_loop_matches_oracle(oracle_lib, product_lib):
         assert np.abs(To - Tg).max() < 1e-6 * max(1.0, np.abs(To).max()), np.abs(To - Tg).max()
         poses_o.append(To); poses_g.append(Tg)
     assert len(poses_g) == 3
+
+
+def test_pipeline_depth16_wraps_around(product_lib):
+    """20 frames through 16 pipeline slots (slots, window vectors and result buffers get recycled) == strictly sequential."""
+    s = [synth.make_stream("hkust", seed=6, n_seeds=800, t_ts=0.50 + 0.01 * k, history_ms=10.0) for k in range(20)]
+    ref = None
+    for depth in (1, 16):
+        def tw(p):
+            p.max_num_fusion_frames = 5
+        g = _gpu_backend(product_lib, "hkust", tweak=tw)
+        g.set_pipeline_depth(depth)
+        tickets, got = [], []
+        for f in s:
+            if len(tickets) >= max(1, depth - 1):
+                m, c = g.results_end(tickets.pop(0)); got.append((c, m.tobytes()))
+            for cam, side in ((0, "left"), (1, "right")):
+                e = f[side]
+                g.stage_ts_events(cam, e["x"], e["y"], e["t"], e["p"])
+                g.run_ts_build(cam, f["t_ts_ns"])
+            T = np.ascontiguousarray(f["T_world_left"], np.float64)
+            g._call("set_ts_pair_dev", [C.POINTER(C.c_double)], T.ctypes.data_as(C.POINTER(C.c_double)))
+            sd = f["seeds"]
+            g.stage_mapping_inputs(sd["x"], sd["y"], sd["t"], f["pose_t"], f["poses"])
+            g.run_mapping()
+            tickets.append(g.results_begin())
+        while tickets:
+            m, c = g.results_end(tickets.pop(0)); got.append((c, m.tobytes()))
+        assert len(got) == len(s)
+        if ref is None:
+            ref = got
+            assert sum(c["n_fusions"] for c, _ in ref) > 0 and ref[-1][0]["map_size"] > 100
+        else:
+            assert [a[0] for a in got] == [a[0] for a in ref]
+            assert [a[1] for a in got] == [a[1] for a in ref], "depth 16 changed the maps"
