@@ -31,6 +31,8 @@ def _worker(rank, world, port, q):
     rec = edist.make_record(seed, 1, c, edist.map_checksum(o.map_download()))
     local_ms = 10.0 + 5.0 * rank
     mx, tot, recs = edist.reduce_and_gather(local_ms, c["bm_evals"] + c["lm_evals"], rec)
+    per_rank = edist.gather_scalars([local_ms, float(rank)])          # bench.py's per-rank diagnostics
+    assert per_rank.shape == (world, 2) and list(per_rank[:, 0]) == [10.0, 15.0] and list(per_rank[:, 1]) == [0.0, 1.0]
     q.put((rank, mx, tot, recs, c["bm_evals"] + c["lm_evals"]))
     dist.destroy_process_group()
 
