@@ -15,7 +15,7 @@
 
 namespace esvo {
 
-constexpr int BM_WARPS = 4;
+constexpr int BM_WARPS = 1;   // one event per block (2.5 K registers): fits the hole a retiring LM block leaves (fuse.cu: fuse_finish)
 constexpr int BM_MAXC = 192;  // max coarse candidates per event kept in shared memory
 
 struct BmArgs {
@@ -240,7 +240,7 @@ int bm_run(Ctx* c) {
 }
 
 int seeds_order(Ctx* c) {
-  seeds_order_kernel<<<1, 1024, 0, c->stream>>>(c->dc, c->bm, c->d_ex, c->d_ey, c->d_et, c->d_poses, (int)c->n_ev,
+  seeds_order_kernel<<<1, kOrderThreads, 0, c->stream>>>(c->dc, c->bm, c->d_ex, c->d_ey, c->d_et, c->d_poses, (int)c->n_ev,
                                                 c->d_seeds, (unsigned long long*)c->d_counters);
   c->launches += 1;
   ESVO_CUDA_TRY(c, cudaGetLastError());

@@ -584,7 +584,7 @@ int fuse_points(Ctx* c, const esvo_depth_point* d_pts, size_t n_cap, const uint6
     int rc = prop_reserve(c, n_cap);
     if (rc) return rc;
   }
-  const int B = 128;
+  const int B = 64;    // 64 registers x 64 threads = one LM block's worth (see fuse_finish)
   FrameSet fs;
   fs.nframes = 1; fs.pts[0] = d_pts; fs.cnt[0] = (const unsigned long long*)d_n; fs.cap[0] = (int)n_cap; fs.off[0] = 0; fs.off[1] = (int)n_cap;
   DevConsts dcs = c->dc;
@@ -600,7 +600,7 @@ int fuse_points(Ctx* c, const esvo_depth_point* d_pts, size_t n_cap, const uint6
 // Stage a whole window (vectors given newest first) with as few launches as possible.
 int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
   MapState* ms = c->map;
-  const int B = 128;
+  const int B = 64;
   for (int f0 = 0; f0 < nframes; f0 += FS_MAX) {
     FrameSet fs;
     fs.nframes = std::min(FS_MAX, nframes - f0);
@@ -623,7 +623,10 @@ int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
 int fuse_finish(Ctx* c, bool naive) {
   MapState* ms = c->map;
   if (ms->staged == 0) return ESVO_OK;
-  const int npix = c->dc.W * c->dc.H, B = 128;
+  // 32-thread blocks (3.4 K registers): a fold block fits into the hole ONE retiring LM block (4 K registers) leaves on
+  // an SM.  With 128-thread blocks (13 K registers) the fold starved behind the LM blocks of the other pipeline slots,
+  // which refill every hole at once: 2-3 ms per frame instead of 0.3 ms (timeline of the 16-slot pipeline).
+  const int npix = c->dc.W * c->dc.H, B = 32;
   if (naive) fuse_fold_kernel<true><<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->seq_base, ms->d_scal);
   else fuse_fold_kernel<false><<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->seq_base, ms->d_scal);
   c->launches += 1;
@@ -641,7 +644,7 @@ int map_clean(Ctx* c, double var_thr, double age_thr, double rmax, double rmin) 
 }
 
 int map_regularize(Ctx* c) {
-  const int npix = c->dc.W * c->dc.H, B = 128;
+  const int npix = c->dc.W * c->dc.H, B = 32;   // 69 registers: small blocks for the same reason as the fold
   map_regularize_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, c->map->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
                                                               c->prm.reg_min_close_neighbours);
   map_regularize_commit_kernel<<<div_up(npix, 256), 256, 0, c->stream>>>(npix, c->map->m);
