@@ -79,6 +79,10 @@ class TimeSurface {
     return esvo_ts_build(cs_->ctx(), cam_, external_sync_time_ns, nullptr, time_surface_out) == ESVO_OK;
   }
   void clearEventQueue() { esvo_ts_reset(cs_->ctx(), cam_); }
+  // The reference tolerates stamps that arrive out of order (its insertion sort then re-queues events_.back(),
+  // TimeSurface.cpp:410-422).  Off by default here (drivers deliver ordered packets; saves two kernels per push);
+  // switch it on for sources that do not guarantee ordering -- results are then identical to the reference's.
+  bool setUnorderedInput(bool enable) { return esvo_ts_set_unordered_input(cs_->ctx(), cam_, enable ? 1 : 0) == ESVO_OK; }
  private:
   esvo::CameraSystem::Ptr cs_;
   int cam_;
