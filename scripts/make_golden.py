@@ -93,5 +93,53 @@ def main():
     print("bm seeds", seeds.size, "lm points", pts.size, "map", m1.size, m2.size, "track", st)
 
 
+def extras():
+    """tests/golden/extras.npz: outputs of the oracle for the paths added after the first fixture -- FORWARD time surface,
+    out-of-order stamps, initialisation from an SGM disparity map -- on the inputs of small_rig_frame.npz."""
+    import ast
+    import cv2
+    z = np.load(os.path.join(OUT, "small_rig_frame.npz"), allow_pickle=False)
+    configs.RIGS["golden_small"] = ast.literal_eval(bytes(z["rig_json"]).decode())
+    lib = capi.load_oracle()
+    l, r = configs.rig_calibs("golden_small")
+
+    def backend(tweak=None):
+        p = configs.params_for("hkust", lib)
+        if tweak:
+            tweak(p)
+        b = capi.Backend(lib, l, r, p)
+        b.set_rectify_tables(0, z["map1_l"], z["map2_l"], z["lut_l"], z["mask_l"])
+        b.set_rectify_tables(1, z["map1_r"], z["map2_r"], z["lut_r"], z["mask_r"])
+        return b
+
+    ev, t = z["ev_left"], z["evt_left"]
+    # FORWARD mode, polarity on, median 3x3
+    def fw(p):
+        p.time_surface_mode = 1; p.ignore_polarity = 0
+    o = backend(fw)
+    o.ts_push_events(0, ev[0], ev[1], t, ev[2].astype(np.uint8))
+    _, fwd_T = o.ts_build(0, int(z["t_ts_ns"]))
+    _, fwd_mid = o.ts_build(0, int(z["t_mid_ns"]))
+    # out-of-order stamps: every 11th event arrives 0.3 ms "late"
+    tj = t.copy(); tj[5::11] -= 300_000
+    o = backend()
+    o.ts_push_events(0, ev[0], ev[1], tj, ev[2].astype(np.uint8))
+    un_idx, un_ts = o.ts_build(0, int(z["t_ts_ns"]))
+    un_idx_mid, un_ts_mid = o.ts_build(0, int(z["t_mid_ns"]))
+    # initialisation from the SGM disparity of the golden TS pair (cv::StereoSGBM with the reference's parameters)
+    H, W = z["ts_left"].shape
+    disp = cv2.StereoSGBM_create(0, 48, 11, 8 * 11 * 11, 32 * 11 * 11, -1, 0, 11).compute(z["ts_left"], z["ts_right"])
+    o = backend()
+    n, acc = o.init_from_disparity(disp, z["seeds_xy"][0], z["seeds_xy"][1], z["T_world_left"], 20)
+    assert acc, n
+    np.savez_compressed(os.path.join(OUT, "extras.npz"), fwd_T=fwd_T, fwd_mid=fwd_mid, t_jitter=tj, un_idx=un_idx.astype(np.int32), un_ts=un_ts,
+                        un_idx_mid=un_idx_mid.astype(np.int32), un_ts_mid=un_ts_mid, disp16=disp.astype(np.int16), sgm_n=np.int64(n),
+                        sgm_points=o.window_download(0), sgm_map=o.map_download())
+    print("wrote", os.path.join(OUT, "extras.npz"), os.path.getsize(os.path.join(OUT, "extras.npz")), "bytes; sgm points", n)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "extras":
+        extras()
+    else:
+        main()

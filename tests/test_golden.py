@@ -84,3 +84,39 @@ def test_oracle_reproduces_golden(oracle_lib):
 def test_cuda_path_reproduces_golden(product_lib):
     z = _load()
     _run(_backend(product_lib, z), z, exact=False)
+
+
+def test_oracle_reproduces_golden_extras(oracle_lib):
+    """tests/golden/extras.npz (scripts/make_golden.py extras): FORWARD time surface, out-of-order stamps, initialisation
+    from an SGM disparity map -- the oracle still reproduces them bit for bit."""
+    z = _load()
+    x = np.load(os.path.join(os.path.dirname(GOLD), "extras.npz"), allow_pickle=False)
+    l, r = configs.rig_calibs("golden_small")
+
+    def backend(tweak=None):
+        p = configs.params_for("hkust", oracle_lib)
+        if tweak:
+            tweak(p)
+        b = capi.Backend(oracle_lib, l, r, p)
+        b.set_rectify_tables(0, z["map1_l"], z["map2_l"], z["lut_l"], z["mask_l"])
+        b.set_rectify_tables(1, z["map1_r"], z["map2_r"], z["lut_r"], z["mask_r"])
+        return b
+
+    ev, t = z["ev_left"], z["evt_left"]
+    def fw(p):
+        p.time_surface_mode = 1; p.ignore_polarity = 0
+    o = backend(fw)
+    o.ts_push_events(0, ev[0], ev[1], t, ev[2].astype(np.uint8))
+    assert np.array_equal(o.ts_build(0, int(z["t_ts_ns"]))[1], x["fwd_T"])
+    assert np.array_equal(o.ts_build(0, int(z["t_mid_ns"]))[1], x["fwd_mid"])
+    o = backend()
+    o.ts_push_events(0, ev[0], ev[1], x["t_jitter"], ev[2].astype(np.uint8))
+    i1, s1 = o.ts_build(0, int(z["t_ts_ns"])); i2, s2 = o.ts_build(0, int(z["t_mid_ns"]))
+    assert np.array_equal(i1, x["un_idx"]) and np.array_equal(s1, x["un_ts"])
+    assert np.array_equal(i2, x["un_idx_mid"]) and np.array_equal(s2, x["un_ts_mid"])
+    assert (x["un_idx"] != z["idx_left"]).any()            # the jitter does change which arrival a pixel reports
+    o = backend()
+    n, acc = o.init_from_disparity(x["disp16"], z["seeds_xy"][0], z["seeds_xy"][1], z["T_world_left"], 20)
+    assert acc and n == int(x["sgm_n"])
+    assert o.window_download(0).tobytes() == x["sgm_points"].tobytes()
+    assert o.map_download().tobytes() == x["sgm_map"].tobytes()
