@@ -360,6 +360,23 @@ class Backend:
         keys = ["n_events", "n_seeds", "n_solved", "n_culled", "n_fusions", "bm_evals", "lm_evals", "map_size"]
         return dict(zip(keys, [int(v) for v in ctr]))
 
+    def sgbm_compute(self, left=None, right=None, num_disparities=48, block_size=11, P1=None, P2=None, disp12_max_diff=-1,
+                     pre_filter_cap=0, uniqueness_ratio=11):
+        """cv::StereoSGBM (MODE_SGBM, minDisparity 0) on the device; defaults = the reference's parameters.  left/right None:
+        the observation pair that is on the device."""
+        P1 = 8 * block_size * block_size if P1 is None else P1
+        P2 = 32 * block_size * block_size if P2 is None else P2
+        out = np.zeros((self.H, self.W), np.int16)
+        lp = rp = None
+        if left is not None:
+            l = _arr(left, np.uint8); r = _arr(right, np.uint8)
+            assert l.size == self.W * self.H and r.size == l.size
+            lp, rp = _ptr(l, C.c_uint8), _ptr(r, C.c_uint8)
+        self._call("sgbm_compute", [C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)] + [C.c_int] * 7 + [C.POINTER(C.c_int16)],
+                   lp, rp, int(num_disparities), int(block_size), int(P1), int(P2), int(disp12_max_diff), int(pre_filter_cap),
+                   int(uniqueness_ratio), _ptr(out, C.c_int16))
+        return out
+
     def init_from_disparity(self, disp16, ex, ey, T_world_left, min_points):
         """InitializationAtTime downstream of the SGM call: returns (number of SGM depth points, accepted)."""
         d = _arr(disp16, np.int16); x = _arr(ex, np.uint16); y = _arr(ey, np.uint16)

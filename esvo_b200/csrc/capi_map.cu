@@ -4,12 +4,14 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "sgbm_core.h"
 
 namespace esvo {
 int fuse_zero_fusion_counter(Ctx* c);
 int fuse_fetch_scalars(Ctx* c, unsigned long long out[4]);
 int fuse_reserve(Ctx* c, size_t total_points);
 int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius);
+int sgbm_run(Ctx* c, const uint8_t* d_left, const uint8_t* d_right, int pitch, const esvo_sgbm::Dims& dm, int16_t* d_out);
 
 template <class T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
 
@@ -207,6 +209,37 @@ ESVO_API int esvo_map_download(esvo_ctx* c, esvo_depth_point* out, size_t* n) {
   if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }
   return map_download(c, out, n);
 }
+ESVO_API int esvo_sgbm_compute(esvo_ctx* c, const uint8_t* left, const uint8_t* right, int num_disparities, int block_size, int P1, int P2,
+                               int disp12_max_diff, int pre_filter_cap, int uniqueness_ratio, int16_t* disp16_out) {
+  CHECK_CTX(c);
+  if (!disp16_out || (left == nullptr) != (right == nullptr)) return ESVO_ERR_INVALID_ARG;
+  const int W = c->dc.W, H = c->dc.H;
+  if (num_disparities <= 0 || num_disparities > esvo_sgbm::kMaxD || num_disparities >= W) {
+    c->set_error("esvo_sgbm_compute: numDisparities must be in [1, 128] and smaller than the image width");
+    return ESVO_ERR_UNSUPPORTED;
+  }
+  { int rc0 = drain(c); if (rc0) return rc0; }                     // a one-off at start-up: strictly synchronous
+  const esvo_sgbm::Dims dm = esvo_sgbm::make_dims(W, H, num_disparities, block_size, P1, P2, disp12_max_diff, pre_filter_cap, uniqueness_ratio);
+  uint8_t *d_l = nullptr, *d_r = nullptr; int16_t* d_out = nullptr;
+  const uint8_t *src_l, *src_r; int pitch;
+  auto cleanup = [&]() { cudaFree(d_l); cudaFree(d_r); cudaFree(d_out); };
+  if (dmalloc(&d_out, (size_t)W * H)) { cleanup(); return ESVO_ERR_CUDA; }
+  if (left) {
+    if (dmalloc(&d_l, (size_t)W * H) || dmalloc(&d_r, (size_t)W * H)) { cleanup(); return ESVO_ERR_CUDA; }
+    cudaError_t ce = cudaMemcpyAsync(d_l, left, (size_t)W * H, cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_r, right, (size_t)W * H, cudaMemcpyHostToDevice, c->stream);
+    if (ce != cudaSuccess) { cleanup(); c->set_error(cudaGetErrorString(ce)); return ESVO_ERR_CUDA; }
+    src_l = d_l; src_r = d_r; pitch = W;
+  } else {                                                         // the observation pair that is already on the device
+    if (!c->obs_set) { cleanup(); return ESVO_ERR_STATE; }
+    src_l = c->obs_l; src_r = c->obs_r; pitch = c->dc.pitch;
+  }
+  int rc = sgbm_run(c, src_l, src_r, pitch, dm, d_out);
+  if (rc == ESVO_OK && cudaMemcpy(disp16_out, d_out, (size_t)W * H * 2, cudaMemcpyDeviceToHost) != cudaSuccess) rc = ESVO_ERR_CUDA;
+  cleanup();
+  return rc;
+}
+
 ESVO_API int esvo_init_from_disparity(esvo_ctx* c, const int16_t* disp16, const uint16_t* ex, const uint16_t* ey, size_t n,
                                       const double T[16], size_t min_points, size_t* n_points, int* accepted) {
   CHECK_CTX(c);

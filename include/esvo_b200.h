@@ -237,6 +237,16 @@ ESVO_API int esvo_mapping_at_time(esvo_ctx* ctx, const uint16_t* ex, const uint1
                                   const int64_t* et_ns, size_t n_events,
                                   const int64_t* pose_t_ns, const double* poses, size_t n_poses,
                                   uint64_t* counters_out);
+/* The SGM of esvo_Mapping::InitializationAtTime: cv::StereoSGBM::create(0, numDisparities, blockSize, P1, P2,
+ * disp12MaxDiff, preFilterCap, uniquenessRatio)->compute(left, right, disp) in MODE_SGBM with minDisparity 0
+ * (esvo_core/src/esvo_Mapping.cpp:101-108 uses (0, 48, 11, 8*11*11, 32*11*11, -1, 0, 11); :444 compute).
+ * Bit-exact restatement of OpenCV's integer algorithm on the device (Birchfield-Tomasi cost, 11x11 box aggregation,
+ * five 16-bit path costs, uniqueness + left-right check, 3x3 median).  left/right: H*W mono8 host images, or both NULL to
+ * use the observation pair currently on the device (esvo_set_ts_pair[_dev]).  disp16_out: H*W CV_16S (disparity * 16,
+ * -16 = invalid), host.  Feed it to esvo_init_from_disparity.  numDisparities <= 128. */
+ESVO_API int esvo_sgbm_compute(esvo_ctx* ctx, const uint8_t* left, const uint8_t* right, int num_disparities, int block_size,
+                               int P1, int P2, int disp12_max_diff, int pre_filter_cap, int uniqueness_ratio, int16_t* disp16_out);
+
 /* esvo_Mapping::InitializationAtTime (esvo_core/src/esvo_Mapping.cpp:433-492) downstream of its SGM call, incl.
  * createEdgeMask (:1000-1044, undistorted events, radius 0) and DepthFusion::naive_propagation
  * (esvo_core/src/core/DepthFusion.cpp:232-327).  `disp16` is the H*W CV_16S map cv::StereoSGBM::compute returns

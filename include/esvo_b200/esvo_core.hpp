@@ -377,6 +377,17 @@ class esvo_Mapping {
     if (n_points) *n_points = n;
     return accepted != 0;
   }
+  // Same, with the SGM itself on the device as well (esvo_sgbm_compute: bit-exact restatement of cv::StereoSGBM MODE_SGBM with
+  // the reference's parameters, esvo_Mapping.cpp:101-108) -- no OpenCV needed on the node side.
+  bool InitializationAtTime(const esvo::StampedTimeSurfaceObs& TS_obs, const std::vector<esvo::Event*>& vEventsPtr_left_SGM,
+                            size_t INIT_SGM_DP_NUM_Threshold, size_t* n_points = nullptr) {
+    const int num_disparities = 16 * 3, block_size = 11;                       // esvo_Mapping.cpp:101-105
+    std::vector<int16_t> disp((size_t)cs_->width_ * cs_->height_);
+    if (esvo_sgbm_compute(cs_->ctx(), TS_obs.second.left, TS_obs.second.right, num_disparities, block_size, 8 * block_size * block_size,
+                          32 * block_size * block_size, -1, 0, 11, disp.data()) != ESVO_OK)
+      return false;
+    return InitializationAtTime(TS_obs, disp.data(), vEventsPtr_left_SGM, INIT_SGM_DP_NUM_Threshold, n_points);
+  }
   void reset() { esvo_mapping_reset(cs_->ctx()); }
  private:
   esvo::CameraSystem::Ptr cs_;
