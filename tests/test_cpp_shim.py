@@ -39,3 +39,15 @@ def test_cpp_shim_event_frontend_helpers(tmp_path):
     subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "frontend_check.cpp"), "-o", exe])
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
+
+
+def test_pipelined_c_abi_example_compiles(product_lib, tmp_path):
+    """examples/pipelined_stream.cpp (plain C ABI, S frames in flight): builds with g++; without a GPU it stops at esvo_create."""
+    build = os.path.join(ROOT, "esvo_b200", "_build")
+    exe = str(tmp_path / "pipelined_stream")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "pipelined_stream.cpp"),
+                           "-L" + build, "-lesvo_b200", "-Wl,-rpath," + build, "-o", exe])
+    if has_gpu():
+        return
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 2 and "no CPU fallback" in p.stdout
