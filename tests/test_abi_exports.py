@@ -49,3 +49,14 @@ def test_create_fails_without_device(product_lib):
         assert e.code == -2
     else:
         raise AssertionError("esvo_create must fail without a CUDA device (no CPU fallback)")
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/esvo_b200.h is a C ABI: it must compile as C99 (cgo / JNI / ctypes-style bindings include it from C)."""
+    import subprocess
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "esvo_b200.h"\nint main(void){ esvo_params p; esvo_default_params(&p); '
+                   'return (int)sizeof(esvo_seed) + (int)sizeof(esvo_depth_point) == 0; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                           "-fsyntax-only", str(src)])
