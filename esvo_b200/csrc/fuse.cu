@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) map_rank_permute_kernel(const esvo_depth_
 #pragma unroll 8
     for (unsigned k = 0; k < m; ++k) rank += tile[k] < my ? 1u : 0u;
   }
-  // warp-cooperative copy: 29 lanes move the 29 8-byte words of one element at a time (coalesced PCIe writes)
+  // warp-cooperative copy: WORDS (= 28) lanes move the 8-byte words of one element at a time (coalesced PCIe writes)
   constexpr int WORDS = sizeof(esvo_depth_point) / 8;
   static_assert(sizeof(esvo_depth_point) % 8 == 0 && WORDS <= 32, "element copy assumes <= 32 8-byte words");
   const unsigned lane = threadIdx.x & 31u, wbase = i - lane;
