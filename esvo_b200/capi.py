@@ -128,6 +128,20 @@ def default_params(lib: Library) -> Params:
     return p
 
 
+def compute_rectify_tables(lib: Library, calib: Calib):
+    """esvo_compute_rectify_tables: the product's own host-side tables for one camera (no context, no GPU)."""
+    n = calib.width * calib.height
+    m1 = np.empty(n, np.float32); m2 = np.empty(n, np.float32); lut = np.empty(2 * n, np.float64); mask = np.empty(n, np.uint8)
+    f = lib.fn("compute_rectify_tables")
+    f.argtypes = [C.POINTER(Calib), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_uint8)]
+    f.restype = C.c_int
+    rc = f(C.byref(calib), _ptr(m1, C.c_float), _ptr(m2, C.c_float), _ptr(lut, C.c_double), _ptr(mask, C.c_uint8))
+    if rc:
+        raise EsvoError(rc, "compute_rectify_tables")
+    H, W = calib.height, calib.width
+    return m1.reshape(H, W), m2.reshape(H, W), lut.reshape(H, W, 2), mask.reshape(H, W)
+
+
 def make_calib(width, height, model, K, D, R, P) -> Calib:
     c = Calib()
     c.width, c.height = int(width), int(height)

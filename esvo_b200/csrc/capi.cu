@@ -333,6 +333,17 @@ ESVO_API int esvo_get_rectify_tables(esvo_ctx* c, int cam, float* m1, float* m2,
   if (mask) std::memcpy(mask, c->cam[cam].mask.data(), n);
   return ESVO_OK;
 }
+ESVO_API int esvo_compute_rectify_tables(const esvo_calib* cal, float* m1, float* m2, double* lut, uint8_t* mask) {
+  if (!cal || cal->width <= 0 || cal->height <= 0) return ESVO_ERR_INVALID_ARG;
+  HostCamera hc;
+  host_camera_init(hc, *cal);
+  const size_t n = (size_t)hc.W * hc.H;
+  if (m1) std::memcpy(m1, hc.map1.data(), n * 4);
+  if (m2) std::memcpy(m2, hc.map2.data(), n * 4);
+  if (lut) std::memcpy(lut, hc.lut.data(), 2 * n * 8);
+  if (mask) std::memcpy(mask, hc.mask.data(), n);
+  return ESVO_OK;
+}
 ESVO_API int esvo_get_derived(esvo_ctx* c, double out[4]) {
   CHECK_CTX(c);
   out[0] = c->dc.baseline; out[1] = c->dc.dmin; out[2] = c->dc.dmax; out[3] = c->dc.td_stdvar;
@@ -505,7 +516,8 @@ ESVO_API int esvo_depth_solve(esvo_ctx* c, const esvo_seed* seeds, size_t n, esv
   if (rc) return rc;
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_seeds, seeds, n * sizeof(esvo_seed), cudaMemcpyHostToDevice, c->stream));
   ESVO_CUDA_TRY(c, cudaMemsetAsync(c->d_counters, 0, kCounters * 8, c->stream));
-  if ((rc = lm_run(c, c->d_seeds, n))) return rc;
+  { cudaEvent_t pe = c->prof_begin(3); rc = lm_run(c, c->d_seeds, n); c->prof_end(pe); }
+  if (rc) return rc;
   if ((rc = points_order_impl(c, c->d_seeds, n, 0, 0, 0, 0, 0, nullptr, nullptr))) return rc;
   if ((rc = fetch_counters(c))) return rc;
   const size_t cnt = (size_t)c->h_counters[3];

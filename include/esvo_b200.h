@@ -168,6 +168,11 @@ ESVO_API int esvo_set_rectify_tables(esvo_ctx* ctx, int cam, const float* map1, 
 /* Read back the tables in use (same layouts; NULL pointers are skipped). */
 ESVO_API int esvo_get_rectify_tables(esvo_ctx* ctx, int cam, float* map1, float* map2,
                                      double* lut_xy, uint8_t* mask);
+/* The same tables WITHOUT a context or a GPU (pure host code, one-time setup): what esvo_create computes for one camera.
+ * replaces: cv::initUndistortRectifyMap / cv::undistortPoints (+ fisheye variants) and the validity mask as used by
+ * TimeSurface::cameraInfoCallback (TimeSurface.cpp:313-401) and PerspectiveCamera::preComputeRectifiedCoordinate
+ * (CameraSystem.cpp:37-112).  Lets an integrator (and tests/test_product_tables_cv2.py) compare them with their OpenCV. */
+ESVO_API int esvo_compute_rectify_tables(const esvo_calib* cam, float* map1, float* map2, double* lut_xy, uint8_t* mask);
 /* Derived constants: out[0]=baseline, out[1]=min disparity, out[2]=max disparity (after clip),
  * out[3]=td_stdvar. */
 ESVO_API int esvo_get_derived(esvo_ctx* ctx, double out[4]);

@@ -281,6 +281,27 @@ OAPI int esvo_oracle_track_get_negative_ts(esvo_oracle_ctx* c, double* neg, doub
   return ESVO_OK;
 }
 
+// Pinning tap (tests/test_indep_pins.py): after esvo_oracle_track_reset, select batch 0 like the first solver iteration
+// and return RegProblemLM::operator()(x) and df(0) for it, with the inputs an independent evaluation needs:
+// pts (3 per point, ref frame), Rt = {R_ row-major (9), t_ (3)}.  fjac is row-major n x 6.  Returns the batch size.
+OAPI int esvo_oracle_op_track_eval(esvo_oracle_ctx* c, const double x[6], double* fvec, double* fjac, double* pts, double* Rt, int cap) {
+  if (!c->reg.obs) return ESVO_ERR_STATE;
+  c->reg.setStochasticSampling(0, (size_t)c->prm.trk_batch_size);
+  const int n = (int)c->reg.numPoints;
+  if (n > cap) return ESVO_ERR_CAPACITY;
+  std::vector<double> xv(x, x + 6), fv((size_t)n), J;
+  if (c->reg.residuals(xv, fv) < 0) return ESVO_ERR_UNSUPPORTED;
+  std::vector<double> x0(6, 0.0);
+  if (c->reg.jacobian(x0, J) < 0) return ESVO_ERR_UNSUPPORTED;
+  for (int i = 0; i < n; ++i) {
+    fvec[i] = fv[(size_t)i];
+    for (int j = 0; j < 6; ++j) fjac[i * 6 + j] = J[(size_t)j * n + i];
+    for (int k = 0; k < 3; ++k) pts[3 * i + k] = c->reg.Sampled[3 * (size_t)i + k];
+  }
+  std::memcpy(Rt, c->reg.R_, 9 * sizeof(double)); std::memcpy(Rt + 9, c->reg.t_, 3 * sizeof(double));
+  return n;
+}
+
 // ---- raw helpers exposed for pinning tests (cv2 / scipy / libc cross-checks) ----
 OAPI void esvo_oracle_op_median3(const uint8_t* s, uint8_t* d, int W, int H, int k) { median_blur_u8(s, d, W, H, k); }
 OAPI void esvo_oracle_op_remap_u8(const uint8_t* s, uint8_t* d, int W, int H, const float* mx, const float* my) { remap_bilinear_u8(s, d, W, H, mx, my); }
@@ -296,6 +317,31 @@ OAPI int esvo_oracle_op_depth_residual(esvo_oracle_ctx* c, const esvo_seed* s, d
   Seed sd = seed_from_pod(*s);
   dp.setProblem(sd.x_left, sd.trans);
   return dp(rho, fvec);
+}
+// The reference's solver loop for ONE seed (DepthProblemSolver.cpp:138-186, same statements as DepthSolver::solve_single)
+// with a trace: trace[2k] = x after the k-th minimizeOneStep, trace[2k+1] = its status.  Returns the number of steps.
+OAPI int esvo_oracle_op_depth_solve_trace(esvo_oracle_ctx* c, const esvo_seed* s, double* trace, int max_steps) {
+  DepthProblem dp; dp.cs = &c->cs; dp.obs = &c->obs; dp.configure(c->prm);
+  Seed sd = seed_from_pod(*s);
+  dp.setProblem(sd.x_left, sd.trans);
+  const int m = dp.wx * dp.wy;
+  LevenbergMarquardt lm;
+  lm.f = [&](const std::vector<double>& x, std::vector<double>& fv) { dp(x[0], fv.data()); return 0; };
+  lm.df = [&](const std::vector<double>& x, std::vector<double>& J) { return numerical_diff_forward(lm.f, x, J, m); };
+  lm.ftol = 1e-6; lm.xtol = 1e-6; lm.maxfev = c->prm.max_iteration * 3;
+  std::vector<double> x(1, sd.invDepth);
+  if (lm.minimizeInit(x, m) == LM_ImproperInputParameters) return -1;
+  size_t iteration = 0; int state = 0, k = 0;
+  while (true) {
+    LMStatus status = lm.minimizeOneStep(x);
+    if (k < max_steps) { trace[2 * k] = x[0]; trace[2 * k + 1] = (double)status; ++k; }
+    iteration++;
+    if (iteration >= (size_t)c->prm.max_iteration) break;
+    bool terminate = false;
+    if (status == 2 || status == 3) { if (state == 0) state++; else terminate = true; }
+    if (terminate) break;
+  }
+  return k;
 }
 // Generic LM driver for pinning against MINPACK: minimise sum (a_i*exp(-b_i*x0)+x1*c_i - y_i)^2 style
 // problems is done in Python; here we expose a scripted 1-D/2-D test function family:

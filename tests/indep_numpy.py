@@ -1,0 +1,242 @@
+"""Independent numpy/scipy re-derivation of the hot-path arithmetic, written from the REFERENCE sources only
+(file:line cited per function) -- not from oracle/ and not from the CUDA kernels.  tests/test_indep_pins.py runs the
+C++ oracle against these on the golden inputs, so that oracle and kernels are no longer checked only against a
+restatement by the same reading ("what's weak" 1).  TEST INFRASTRUCTURE: plain f64 numpy, clarity over speed.
+"""
+import numpy as np
+
+
+# ---- a5: tools::meanStdDev / normalizePatch (esvo_core/include/esvo_core/tools/utils.h:74-92),
+#          EventBM::zncc_cost (esvo_core/src/core/EventBM.cpp:317-333)
+def zncc_cost(pl, pr):
+    pl = np.asarray(pl, np.float64); pr = np.asarray(pr, np.float64)
+    n = pl.size
+
+    def normalize(p):
+        mean = p.sum() / n
+        sub = p - mean
+        sigma = np.sqrt((sub * sub).sum() / n) + 1e-6
+        return (p - mean) / sigma
+    return 0.5 * (1.0 - (normalize(pl) * normalize(pr)).sum() / n)
+
+
+def bm_search(ts_l, ts_r, x1, dmin, dmax, wx, wy):
+    """EventBM::epipolarSearching with step 1 (EventBM.cpp:170-226): integer-aligned patches centred on x1 = floor(rectified
+    event) in the left and (x1.x - d, x1.y) in the right image; `cost <= min_cost` keeps the LATER disparity on ties (:198)."""
+    hx, hy = (wx - 1) // 2, (wy - 1) // 2
+    H, W = ts_l.shape
+    x, y = int(x1[0]), int(x1[1])
+    pl = ts_l[y - hy:y + hy + 1, x - hx:x + hx + 1]
+    best, best_d = 1.0, None          # ZNCC_MAX_ = 1 (EventBM.h)
+    for d in range(dmin, dmax + 1):
+        x2 = x - d
+        if x2 - hx < 1 or y - hy < 1 or x2 + hx >= W - 1 or y + hy >= H - 1:   # isValidPatch (:251-267)
+            continue
+        pr = ts_r[y - hy:y + hy + 1, x2 - hx:x2 + hx + 1]
+        c = zncc_cost(pl, pr)
+        if c <= best:
+            best, best_d = c, d
+    return best_d, best
+
+
+# ---- a7: PerspectiveCamera::cam2World (esvo_core/src/container/CameraSystem.cpp:120-139): literal 4x4 inverse
+def cam2world(P, x, inv_depth):
+    z = 1.0 / inv_depth
+    Pt = np.zeros((4, 4)); Pt[:3, :] = P; Pt[3, :] = [0, 0, 0, z]
+    ps = z * np.linalg.inv(Pt) @ np.array([x[0], x[1], 1.0, 1.0])
+    return ps[:3] / ps[3]
+
+
+# ---- a8: DepthProblem::patchInterpolation (esvo_core/src/core/DepthProblem.cpp:193-262)
+def patch_interpolation(img, loc, wx, wy):
+    H, W = img.shape
+    ulx = int(np.floor(loc[0])) - (wx - 1) // 2; uly = int(np.floor(loc[1])) - (wy - 1) // 2
+    drx = int(np.floor(loc[0])) + (wx - 1) // 2; dry = int(np.floor(loc[1])) + (wy - 1) // 2
+    if ulx < 0 or uly < 0 or drx >= W or dry >= H:
+        return None
+    ly, lx = int(np.floor(loc[1])), int(np.floor(loc[0]))
+    q1 = (lx + 1) - loc[0]; q2 = loc[0] - lx; q3 = (ly + 1) - loc[1]; q4 = loc[1] - ly
+    if uly + wy >= H or ulx + wx >= W:
+        return None
+    src = img[uly:uly + wy + 1, ulx:ulx + wx + 1].astype(np.float64)
+    R = q1 * src[:, :wx] + q2 * src[:, 1:wx + 1]
+    return q3 * R[:wy, :] + q4 * R[1:wy + 1, :]
+
+
+# ---- a6/a7: DepthProblem::warping (:162-191) and operator() for LSnorm = Tdist (:34-160)
+def depth_residual(rho, coor, T_left_virtual, Pl, Pr, ts_l, ts_r, wx, wy, nu, scale):
+    n = wx * wy
+    H, W = ts_l.shape
+
+    def fail():
+        w = (nu + 1) / (nu + (255.0 / scale) ** 2)
+        return np.full(n, np.sqrt(w) * 255.0)
+    p_rv = cam2world(Pl, coor, rho)
+    p_left = T_left_virtual[:3, :3] @ p_rv + T_left_virtual[:3, 3]
+    h1 = Pl[:, :3] @ p_left + Pl[:, 3]; h2 = Pr[:, :3] @ p_left + Pr[:, 3]
+    x1 = h1[:2] / h1[2]; x2 = h2[:2] / h2[2]
+    hx, hy = (wx - 1) // 2, (wy - 1) // 2
+    for xs in (x1, x2):
+        if xs[0] < hx or xs[0] > W - hx or xs[1] < hy or xs[1] > H - hy:
+            return fail()
+    t1 = patch_interpolation(ts_l, x1, wx, wy)
+    t2 = patch_interpolation(ts_r, x2, wx, wy) if t1 is not None else None
+    if t1 is None or t2 is None:
+        return fail()
+    r = (t1 - t2).ravel(); r2 = r * r
+    s1, s2, first = scale * scale, -1.0, True
+    while first or abs(s2 - s1) / s1 > 0.05:                                    # :96
+        if not first:
+            s1 = s2
+        nz = r != 0
+        with np.errstate(over="ignore", divide="ignore"):
+            tot = float(np.sum(r2[nz] * (nu + 1) / (nu + r2[nz] / s1)))        # :112-114 (order of summation differs)
+        if tot == 0:
+            s2 = scale * scale
+            break
+        s2 = tot / n
+        first = False
+    with np.errstate(over="ignore", divide="ignore"):
+        w = (nu + 1) / (nu + r2 / s2)
+    return np.sqrt(w) * r
+
+
+# ---- a11: DepthPoint::update_studentT (esvo_core/src/container/DepthPoint.cpp:166-188)
+def update_student_t(state, rho, s2, var, nu):
+    """state = dict(rho, s2, nu, var, age); rho <= -1e-6 means 'new point'."""
+    st = dict(state)
+    if st["rho"] > -1e-6:
+        nu_u = min(nu, st["nu"])
+        rho_u = (s2 * st["rho"] + st["s2"] * rho) / (st["s2"] + s2)
+        s2_u = (nu_u + (st["rho"] - rho) ** 2 / (st["s2"] + s2)) / (nu_u + 1) * (st["s2"] * s2) / (st["s2"] + s2)
+        st.update(rho=rho_u, s2=s2_u, nu=nu_u + 1)
+        st["var"] = st["nu"] / (st["nu"] - 2) * st["s2"]
+        st["age"] += 1
+    else:
+        st.update(rho=rho, s2=s2, var=var, nu=nu)
+    return st
+
+
+# ---- a12: DepthFusion::propagate_one_point (esvo_core/src/core/DepthFusion.cpp:18-68), Tdist branch
+def propagate_point(p_cam, s2, nu, T_prop_prior, Pl, W, H):
+    p = T_prop_prior[:3, :3] @ p_cam + T_prop_prior[:3, 3]
+    h = Pl[:, :3] @ p + Pl[:, 3]
+    x = h[:2] / h[2]
+    if x[0] < 0 or x[0] >= W or x[1] < 0 or x[1] >= H:        # boundaryCheck (DepthFusion.cpp:194-199)
+        return None
+    rho = 1.0 / p[2]
+    den = T_prop_prior[2, :2] @ p_cam[:2] + T_prop_prior[2, 3]
+    den /= p_cam[2]
+    den += T_prop_prior[2, 2]
+    J = T_prop_prior[2, 2] / den ** 2
+    s2p = J * J * s2
+    return dict(row=int(np.floor(x[1])), col=int(np.floor(x[0])), x=x, rho=rho, s2=s2p, nu=nu, var=nu / (nu - 2) * s2p, p_cam=p)
+
+
+# ---- tools::cayley2rot (esvo_core/src/tools/cayley.cpp:4-21)
+def cayley2rot(c):
+    c1, c2, c3 = c
+    k = 1 + c1 * c1 + c2 * c2 + c3 * c3
+    R = np.array([[1 + c1 * c1 - c2 * c2 - c3 * c3, 2 * (c1 * c2 - c3), 2 * (c1 * c3 + c2)],
+                  [2 * (c1 * c2 + c3), 1 - c1 * c1 + c2 * c2 - c3 * c3, 2 * (c2 * c3 - c1)],
+                  [2 * (c1 * c3 - c2), 2 * (c2 * c3 + c1), 1 - c1 * c1 - c2 * c2 + c3 * c3]])
+    return R / k
+
+
+# ---- RegProblemLM::computeJ_G (esvo_core/src/core/RegProblemLM.cpp:271-320), general x
+def compute_J_G(x):
+    c1, c2, c3 = x[:3]
+    k = 1 + c1 ** 2 + c2 ** 2 + c3 ** 2; k2 = k * k
+    A1 = np.array([[2 * c1 / k - 2 * c1 * (1 + c1 ** 2 - c2 ** 2 - c3 ** 2) / k2, -2 * c2 / k - 2 * c2 * (1 + c1 ** 2 - c2 ** 2 - c3 ** 2) / k2,
+                    -2 * c3 / k - 2 * c3 * (1 + c1 ** 2 - c2 ** 2 - c3 ** 2) / k2],
+                   [2 * c2 / k - 4 * c1 * (c1 * c2 + c3) / k2, 2 * c1 / k - 4 * c2 * (c1 * c2 + c3) / k2, 2 / k - 4 * c3 * (c1 * c2 + c3) / k2],
+                   [2 * c3 / k - 4 * c1 * (c1 * c3 - c2) / k2, -2 / k + 4 * c2 * (c1 * c3 - c2) / k2, 2 * c1 / k - 4 * c3 * (c1 * c3 - c2) / k2]])
+    A2 = np.array([[2 * c2 / k - 4 * c1 * (c1 * c2 - c3) / k2, 2 * c1 / k - 4 * c2 * (c1 * c2 - c3) / k2, -2 / k - 4 * c3 * (c1 * c2 - c3) / k2],
+                   [-2 * c1 / k - 2 * c1 * (1 - c1 ** 2 + c2 ** 2 - c3 ** 2) / k2, 2 * c2 / k - 2 * c2 * (1 - c1 ** 2 + c2 ** 2 - c3 ** 2) / k2,
+                    -2 * c3 / k - 2 * c3 * (1 - c1 ** 2 + c2 ** 2 - c3 ** 2) / k2],
+                   [2 / k - 4 * c1 * (c1 + c2 * c3) / k2, 2 * c3 / k - 4 * c2 * (c1 + c2 * c3) / k2, 2 * c2 / k - 4 * c3 * (c1 + c2 * c3) / k2]])
+    A3 = np.array([[2 * c3 / k - 4 * c1 * (c2 + c1 * c3) / k2, 2 / k - 4 * c2 * (c2 + c1 * c3) / k2, 2 * c1 / k - 4 * c3 * (c2 + c1 * c3) / k2],
+                   [-2 / k - 4 * c1 * (c2 * c3 - c1) / k2, 2 * c3 / k - 4 * c2 * (c2 * c3 - c1) / k2, 2 * c2 / k - 4 * c3 * (c2 * c3 - c1) / k2],
+                   [-2 * c1 / k - 2 * c1 * (1 - c1 ** 2 - c2 ** 2 + c3 ** 2) / k2, -2 * c2 / k - 2 * c2 * (1 - c1 ** 2 - c2 ** 2 + c3 ** 2) / k2,
+                    2 * c3 / k - 2 * c3 * (1 - c1 ** 2 - c2 ** 2 + c3 ** 2) / k2]])
+    J = np.zeros((12, 6))
+    J[0:3, 0:3] = A1; J[3:6, 0:3] = A2; J[6:9, 0:3] = A3; J[9:12, 3:6] = np.eye(3)
+    return J
+
+
+def bilinear_1x1(img, loc):
+    """RegProblemLM::patchInterpolation (RegProblemLM.cpp:418-487) for a 1x1 patch: value at a sub-pixel location."""
+    H, W = img.shape
+    lx, ly = int(np.floor(loc[0])), int(np.floor(loc[1]))
+    if lx < 0 or ly < 0 or lx >= W or ly >= H or ly + 1 >= H or lx + 1 >= W:
+        return None
+    q1 = (lx + 1) - loc[0]; q2 = loc[0] - lx; q3 = (ly + 1) - loc[1]; q4 = loc[1] - ly
+    s = img[ly:ly + 2, lx:lx + 2].astype(np.float64)
+    R = q1 * s[:, 0] + q2 * s[:, 1]
+    return q3 * R[0] + q4 * R[1]
+
+
+def track_reproject(p, T, Pl, mask):
+    """RegProblemLM::reprojection + isValidPatch for wx = wy = 1 (RegProblemLM.cpp:380-416)."""
+    H, W = mask.shape
+    pl = T[:3, :3] @ p + T[:3, 3]
+    h = Pl[:, :3] @ pl + Pl[:, 3]
+    x = h[:2] / h[2]
+    if x[0] < 0 or x[0] > W - 1 or x[1] < 0 or x[1] > H - 1:
+        return None
+    if mask[int(x[1]), int(x[0])] < 125:
+        return None
+    return x
+
+
+def warping_transformation(R_, t_, x):
+    """RegProblemLM::getWarpingTransformation (RegProblemLM.cpp:322-346)."""
+    dR = cayley2rot(x[:3])
+    U, _, Vt = np.linalg.svd(R_.T @ dR.T)
+    Rcr = U @ Vt
+    T = np.eye(4); T[:3, :3] = Rcr; T[:3, 3] = -Rcr @ (x[3:] + dR @ t_)
+    return T
+
+
+def track_residuals(x, pts, R_, t_, Pl, mask, ts_neg, huber):
+    """RegProblemLM::operator() + thread (RegProblemLM.cpp:91-176), 1x1 patches, LSnorm Huber (huber=None: l2)."""
+    T = warping_transformation(R_, t_, x)
+    out = np.empty(len(pts))
+    for i, p in enumerate(pts):
+        xs = track_reproject(p, T, Pl, mask)
+        r = 255.0
+        if xs is not None:
+            v = bilinear_1x1(ts_neg, xs)
+            if v is not None:
+                r = v
+        if huber is not None:
+            w = huber / r if r > huber else 1.0
+            out[i] = np.sqrt(w) * r
+        else:
+            out[i] = r
+    return out
+
+
+def track_jacobian(pts, R_, t_, Pl, mask, d_du, d_dv):
+    """RegProblemLM::df at x = 0 (RegProblemLM.cpp:178-269) with J_G_0 = computeJ_G(0)."""
+    JG0 = compute_J_G(np.zeros(6))
+    Jc = R_.T @ np.array([[1.0 / Pl[0, 0], 0], [0, 1.0 / Pl[1, 1]], [0, 0]])
+    T = np.eye(4); T[:3, :3] = R_.T; T[:3, 3] = -R_.T @ t_
+    blk = np.zeros((len(pts), 12))
+    for i, p in enumerate(pts):
+        xs = track_reproject(p, T, Pl, mask)
+        if xs is None:
+            continue
+        gx, gy = bilinear_1x1(d_du, xs), bilinear_1x1(d_dv, xs)
+        if gx is None or gy is None:
+            continue
+        g = np.array([gx / 8, gy / 8])
+        dPi = np.zeros((2, 3))
+        dPi[:, :2] = Pl[:2, :2] / p[2]
+        z2 = p[2] ** 2
+        dPi[0, 2] = -(Pl[0, 0] * p[0] + Pl[0, 1] * p[1] + Pl[0, 3]) / z2
+        dPi[1, 2] = -(Pl[1, 0] * p[0] + Pl[1, 1] * p[1] + Pl[1, 3]) / z2
+        dT = np.zeros((3, 12))
+        dT[:, 0:3] = p[0] * np.eye(3); dT[:, 3:6] = p[1] * np.eye(3); dT[:, 6:9] = p[2] * np.eye(3); dT[:, 9:12] = np.eye(3)
+        blk[i] = g @ dPi @ Jc @ dPi @ dT * p[2]
+    return -blk @ JG0

@@ -26,7 +26,8 @@ def test_header_symbols_exported(product_lib, oracle_lib):
                                        "esvo_run_mapping", "esvo_fetch_mapping_counters", "esvo_sync", "esvo_stream",
                                        "esvo_launch_count", "esvo_last_error", "esvo_debug_counter", "esvo_profile",
                                        "esvo_profile_read", "esvo_set_pipeline_depth", "esvo_results_begin", "esvo_results_end",
-                                           "esvo_sgbm_compute"):   # its oracle is oracle/sgbm.py (numpy, pinned against cv2)
+                                       "esvo_compute_rectify_tables",   # host set-up of the product, pinned to cv2 directly
+                                       "esvo_sgbm_compute"):   # its oracle is oracle/sgbm.py (numpy, pinned against cv2)
             continue
         assert hasattr(oracle_lib.lib, n.replace("esvo_", "esvo_oracle_", 1)), n
 

@@ -1,0 +1,266 @@
+"""Pins the C++ oracle (and through it the CUDA path) against an INDEPENDENT numpy/scipy f64 re-derivation of
+a5 / a6-a8 / a9 / a11 / a12 / a17 / a18 written from the reference sources only (tests/indep_numpy.py), on the
+golden scenario.  SURVEY 8c lists exactly these cross-checks; VERDICT r1 "next round" item 2.
+  * a5  zncc cost and best disparity            vs EventBM (oracle bm_match)
+  * a6  DepthProblem residual vector (Tdist)    vs oracle op_depth_residual
+  * a9  MINPACK lmdif (scipy.optimize.leastsq) on the numpy residual vs oracle depth_solve (rho, variance)
+  * a11/a12 propagate + Student-t update        vs oracle fuse
+  * a17/a18 tracking residual / Jacobian        vs oracle RegProblem (tap esvo_oracle_op_track_eval)
+  * KAT: cayley2rot(0) = I, computeJ_G(0), dR/dc by finite differences
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import indep_numpy as ind
+from esvo_b200 import capi, configs
+from util import build_ts_pair, scenario
+
+scipy_opt = pytest.importorskip("scipy.optimize")
+
+RIG = "hkust"
+
+
+@pytest.fixture(scope="module")
+def frame(oracle_lib):
+    s = scenario(RIG, seed=2, n_seeds=1500)
+    l, r = configs.rig_calibs(RIG)
+    prm = configs.params_for(RIG, oracle_lib)
+    o = capi.Backend(oracle_lib, l, r, prm)
+    tl, tr = build_ts_pair(o, s)
+    o.set_ts_pair(tl, tr, s["T_world_left"])
+    sd = s["seeds"]
+    seeds, _ = o.bm_match(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+    cams = configs.rig_arrays(RIG)
+    return dict(o=o, s=s, tl=tl, tr=tr, seeds=seeds, prm=prm, Pl=cams["left"]["P"], Pr=cams["right"]["P"], d=o.get_derived())
+
+
+def test_bm_cost_and_disparity_vs_numpy(frame):
+    f = frame
+    seeds = f["seeds"]
+    assert seeds.size > 400
+    rng = np.random.default_rng(0)
+    pick = rng.choice(seeds.size, 300, replace=False)
+    for k in pick:
+        sd = seeds[k]
+        x1 = np.floor(sd["x_left"]).astype(int)
+        d, c = ind.bm_search(f["tl"], f["tr"], x1, f["d"]["min_disparity"], f["d"]["max_disparity"], f["prm"].patch_size_x,
+                             f["prm"].patch_size_y)
+        assert d == int(sd["disp"]), (k, d, sd["disp"])
+        assert abs(c - sd["cost"]) < 1e-12, (k, c, sd["cost"])
+        fb = f["d"]["baseline"] * f["Pl"][0, 0]
+        assert abs(sd["inv_depth"] - d / fb) < 1e-15 * max(1.0, d / fb) * 8      # EventBM.cpp:152-158
+        assert sd["x_right"][0] == x1[0] - d and sd["x_right"][1] == x1[1]
+
+
+def _T_left_virtual(f, sd):
+    T_left_world = np.linalg.inv(np.asarray(f["s"]["T_world_left"], float))
+    return T_left_world @ sd["T_world_virtual"].reshape(4, 4)
+
+
+def _oracle_residual(f, sd, rho):
+    fn = f["o"].L.lib.esvo_oracle_op_depth_residual
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+    fn.restype = C.c_int
+    n = f["prm"].patch_size_x * f["prm"].patch_size_y
+    out = np.zeros(n)
+    s1 = np.ascontiguousarray(sd.reshape(1))
+    fn(f["o"].ctx, s1.ctypes.data_as(C.c_void_p), rho, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
+def test_depth_residual_vs_numpy(frame):
+    f = frame
+    prm = f["prm"]
+    rng = np.random.default_rng(1)
+    pick = rng.choice(f["seeds"].size, 120, replace=False)
+    worst = 0.0
+    n_fail = 0
+    for k in pick:
+        sd = f["seeds"][k]
+        T = _T_left_virtual(f, sd)
+        for scale in (1.0, 1.013, 0.97):
+            rho = sd["inv_depth"] * scale
+            a = ind.depth_residual(rho, sd["x_left"], T, f["Pl"], f["Pr"], f["tl"], f["tr"], prm.patch_size_x, prm.patch_size_y,
+                                   prm.td_nu, prm.td_scale)
+            b = _oracle_residual(f, sd, rho)
+            n_fail += np.all(a == a[0])
+            err = np.abs(a - b).max() / max(1.0, np.abs(b).max())
+            worst = max(worst, err)
+            assert err < 1e-9, (k, scale, err)
+    print("depth residual: worst rel deviation numpy vs oracle", worst, "constant (failed-warp) vectors", n_fail)
+    assert n_fail < 0.5 * 3 * pick.size
+
+
+def test_minpack_on_depth_problem_vs_oracle_solve(frame):
+    """scipy.optimize.leastsq = MINPACK lmdif (forward differences, epsfcn=0 -> sqrt(eps), factor 100, ftol = xtol = 1e-6,
+    maxfev 30: DepthProblemSolver.cpp:146-150) on the INDEPENDENT numpy residual, against the oracle's Eigen-LM port inside
+    the reference's solver loop (:160-186).  MINPACK stops at the first convergence report; the reference keeps calling
+    minimizeOneStep until the second one (or 10 steps), so the comparison is made where both exist:
+      * every iterate the oracle accepts up to its first report of status 1/2/3 is a point MINPACK evaluated, and
+        the iterate AT that report is MINPACK's solution (same arithmetic up to the 1e-12 residual differences, which
+        the forward-difference Jacobian amplifies: 1e-6 relative = xtol);
+      * the oracle's final rho (after the extra steps) stays within the solver tolerance of it;
+      * the variance td_stdvar^2 / (J^T J) (:207-211) agrees with MINPACK's covariance at the solution."""
+    f = frame
+    prm = f["prm"]
+    seeds = f["seeds"]
+    pts_o, _ = f["o"].depth_solve(seeds)
+    key = {(float(p["x"][0]), float(p["x"][1]), tuple(np.round(p["T_world_cam"], 12))): p for p in pts_o}
+    tr = f["o"].L.lib.esvo_oracle_op_depth_solve_trace
+    tr.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int]
+    tr.restype = C.c_int
+    rng = np.random.default_rng(2)
+    pick = rng.choice(seeds.size, 330, replace=False)
+    rel_first, rel_final, relv, dev_path = [], [], [], []
+    for k in pick:
+        sd = seeds[k]
+        T = _T_left_virtual(f, sd)
+        calls = []
+
+        def fun(x):
+            calls.append(float(x[0]))
+            return ind.depth_residual(x[0], sd["x_left"], T, f["Pl"], f["Pr"], f["tl"], f["tr"], prm.patch_size_x, prm.patch_size_y,
+                                      prm.td_nu, prm.td_scale)
+        sol, cov, info, msg, ier = scipy_opt.leastsq(fun, [sd["inv_depth"]], full_output=True, ftol=1e-6, xtol=1e-6, gtol=0.0,
+                                                     maxfev=30, factor=100)
+        if ier not in (1, 2, 3):
+            continue                                   # MINPACK ran into maxfev: no first-convergence point to compare
+        trace = np.zeros((16, 2))
+        s1 = np.ascontiguousarray(sd.reshape(1))
+        n = tr(f["o"].ctx, s1.ctypes.data_as(C.c_void_p), trace.ctypes.data_as(C.POINTER(C.c_double)), 16)
+        assert n >= 1
+        conv = [i for i in range(n) if int(trace[i, 1]) in (1, 2, 3)]
+        if not conv:
+            continue
+        i0 = conv[0]
+        calls_a = np.array(calls)
+        # accepted iterates of the port are MINPACK trial points (forward differences with h = 1.5e-8 rho amplify the 1e-12
+        # residual differences between numpy and the oracle, more so along trajectories that travel far)
+        dev_path.append(max(np.abs(calls_a - trace[i, 0]).min() / abs(trace[i, 0]) for i in range(i0 + 1)))
+        rel_first.append(abs(trace[i0, 0] - sol[0]) / abs(sol[0]))
+        p = key.get((float(sd["x_left"][0]), float(sd["x_left"][1]), tuple(np.round(sd["T_world_virtual"], 12))))
+        if p is not None:
+            assert p["inv_depth"] == trace[n - 1, 0]   # the tap replays solve_single exactly
+            rel_final.append(abs(p["inv_depth"] - sol[0]) / abs(sol[0]))
+            if cov is not None and n - 1 == i0:        # same point: J^T J must agree as well
+                var = f["d"]["td_stdvar"] ** 2 * cov[0, 0]
+                relv.append(abs(var - p["variance"]) / abs(p["variance"]))
+    rel_first = np.array(rel_first); rel_final = np.array(rel_final); relv = np.array(relv)
+    print(f"MINPACK vs oracle: compared {rel_first.size}; at first convergence rho rel max {rel_first.max():.2e}; "
+          f"final rho rel median {np.median(rel_final):.2e} max {rel_final.max():.2e}; variance (n={relv.size}) rel max {relv.max() if relv.size else None}")
+    dev_path = np.array(dev_path)
+    print(f"iterate-vs-MINPACK-trial deviation: median {np.median(dev_path):.2e} p98 {np.percentile(dev_path, 98):.2e} max {dev_path.max():.2e}")
+    assert rel_first.size >= 200
+    assert np.median(dev_path) < 1e-8 and np.percentile(dev_path, 98) < 1e-6 and dev_path.max() < 1e-4
+    assert np.median(rel_first) < 1e-8 and np.percentile(rel_first, 98) < 1e-6 and rel_first.max() < 1e-4
+    assert rel_final.max() < 1e-3 and np.percentile(rel_final, 95) < 1e-4
+    if relv.size:
+        assert relv.max() < 1e-4
+
+
+def test_propagate_and_student_t_fusion_vs_numpy(frame):
+    f = frame
+    o, prm = f["o"], f["prm"]
+    pts, _ = o.depth_solve(f["seeds"][:200])
+    W, H = o.W, o.H
+    Tw = np.asarray(f["s"]["T_world_left"], float)
+    # a frame pose slightly away from the observation pose so that the propagation is non-trivial
+    Tf = Tw.copy(); Tf[:3, 3] += [0.004, -0.003, 0.006]
+    checked = fused = 0
+    for p in pts[:60]:
+        o.fuse(p.reshape(1), Tf, 0, True)
+        m = o.map_download()
+        T_prop_prior = np.linalg.inv(Tf) @ p["T_world_cam"].reshape(4, 4)
+        q = ind.propagate_point(p["p_cam"], p["scale2"], p["nu"], T_prop_prior, f["Pl"], W, H)
+        if q is None:
+            assert m.size == 0
+            continue
+        # radius 0 splats (row, col) .. (row+1, col+1) (DepthFusion.cpp:97-121); every created element carries the propagated values
+        assert 1 <= m.size <= 4
+        e = m[0]
+        assert (e["row"], e["col"]) == (q["row"], q["col"])
+        for name, val in (("inv_depth", q["rho"]), ("scale2", q["s2"]), ("nu", q["nu"]), ("variance", q["var"])):
+            assert abs(e[name] - val) <= 1e-12 * abs(val), (name, e[name], val)
+        assert e["residual"] == p["residual"] and e["age"] == p["age"]
+        # pixel centre, p_cam by cam2World at (col+0.5,row+0.5) with the propagated inverse depth (:135-141)
+        pc = ind.cam2world(f["Pl"], [q["col"] + 0.5, q["row"] + 0.5], q["rho"])
+        assert np.abs(e["p_cam"] - pc).max() < 1e-9 * np.abs(pc).max()
+        checked += 1
+        # fuse the same measurement again, perturbed inside the 2-sigma gate: Student-t update (DepthPoint.cpp:166-188)
+        p2 = p.copy()
+        n_f = o.fuse(p2.reshape(1), Tf, 0, False)
+        m2 = o.map_download()
+        if n_f:
+            st = ind.update_student_t(dict(rho=q["rho"], s2=q["s2"], nu=q["nu"], var=q["var"], age=int(p["age"])), q["rho"], q["s2"], q["var"], q["nu"])
+            e2 = m2[0]
+            assert abs(e2["inv_depth"] - st["rho"]) <= 1e-12 * abs(st["rho"])
+            assert abs(e2["scale2"] - st["s2"]) <= 1e-12 * abs(st["s2"]) and e2["nu"] == st["nu"]
+            assert abs(e2["variance"] - st["var"]) <= 1e-12 * abs(st["var"])
+            assert e2["age"] == st["age"] + 1           # update_studentT's age_++ and DepthFusion.cpp:171
+            fused += 1
+    print("propagation checked", checked, "fusions checked", fused)
+    assert checked >= 40 and fused >= 40
+
+
+def test_tracking_residual_and_jacobian_vs_numpy(frame):
+    f = frame
+    o, prm, s = f["o"], f["prm"], f["s"]
+    # a map to track against: the frame's own fused map
+    sd = s["seeds"]
+    o.mapping_reset()
+    o.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+    m = o.map_download()
+    Tw = np.asarray(s["T_world_left"], float)
+    cloud = (m["p_cam"] @ Tw[:3, :3].T + Tw[:3, 3]).astype(np.float32)
+    assert cloud.shape[0] >= prm.trk_batch_size
+    o.track_srand(1)
+    Tc = Tw.copy(); Tc[:3, 3] += [0.002, 0.001, -0.0015]           # prior a little off the reference pose
+    assert o.track_reset(cloud.copy(), Tw, Tc, f["tl"]) == 0
+    neg, du, dv = o.track_get_negative_ts()
+    _, _, _, mask = o.get_rectify_tables(0)
+    fn = o.L.lib.esvo_oracle_op_track_eval
+    fn.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 5 + [C.c_int]
+    fn.restype = C.c_int
+    cap = prm.trk_batch_size
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for x in (np.zeros(6), np.array([0.002, -0.001, 0.0015, 0.003, -0.002, 0.001])):
+        fvec = np.zeros(cap); fjac = np.zeros((cap, 6)); pts = np.zeros((cap, 3)); Rt = np.zeros(12)
+        n = fn(o.ctx, P(np.ascontiguousarray(x)), P(fvec), P(fjac), P(pts), P(Rt), cap)
+        assert n == cap
+        R_, t_ = Rt[:9].reshape(3, 3), Rt[9:]
+        r = ind.track_residuals(x, pts, R_, t_, f["Pl"], mask, neg, prm.trk_huber_threshold)
+        assert np.abs(r - fvec).max() < 1e-9 * 255, np.abs(r - fvec).max()
+        J = ind.track_jacobian(pts, R_, t_, f["Pl"], mask, du, dv)
+        scale = np.abs(J).max()
+        assert scale > 0 and np.abs(J - fjac).max() < 1e-10 * scale, np.abs(J - fjac).max()
+    assert (fvec != 255).mean() > 0.5
+
+
+def test_cayley_and_J_G_kats():
+    # SURVEY 4 KAT table: cayley2rot(0) = I (cayley.cpp:4-21); computeJ_G(0) (RegProblemLM.cpp:271-320)
+    assert np.array_equal(ind.cayley2rot(np.zeros(3)), np.eye(3))
+    J0 = ind.compute_J_G(np.zeros(6))
+    want = np.zeros((12, 6))
+    want[1, 2] = 2; want[2, 1] = -2; want[3, 2] = -2; want[5, 0] = 2; want[6, 1] = 2; want[7, 0] = -2
+    want[9, 3] = want[10, 4] = want[11, 5] = 1
+    assert np.array_equal(J0, want)
+    # the A blocks are d(column j of R)/dc: check against central differences of cayley2rot, at 0 and at a generic point
+    for c0 in (np.zeros(3), np.array([0.11, -0.07, 0.05])):
+        J = ind.compute_J_G(np.concatenate([c0, np.zeros(3)]))
+        h = 1e-6
+        for k in range(3):
+            e = np.zeros(3); e[k] = h
+            dR = (ind.cayley2rot(c0 + e) - ind.cayley2rot(c0 - e)) / (2 * h)
+            for j in range(3):
+                dev = np.abs(J[3 * j:3 * j + 3, k] - dR[:, j])
+                if j == 0 and k == 1 and c0.any():
+                    # reference quirk: A1(2,1) is written "-2/k + 4 c2 (c1 c3 - c2)/k^2" (RegProblemLM.cpp:291); the derivative of
+                    # R(2,0) = 2 (c1 c3 - c2)/k has "-" there.  Harmless: only computeJ_G(0) is ever used (:21), where the term is 0.
+                    assert dev[2] > 1e-3
+                    dev = dev[:2]
+                assert dev.max() < 1e-8
+    # R is orthonormal with det +1 for any Cayley vector
+    R = ind.cayley2rot(np.array([0.3, -0.2, 0.5]))
+    assert np.abs(R @ R.T - np.eye(3)).max() < 1e-15 and abs(np.linalg.det(R) - 1) < 1e-15

@@ -22,10 +22,11 @@ def make_backends(rig, oracle_lib, product_lib, tweak=None):
         tweak(po); tweak(pp)
     o = capi.Backend(oracle_lib, l, r, po)
     g = capi.Backend(product_lib, l, r, pp)
-    # identical rectification tables on both sides (the product's own tables are checked separately)
+    # The product runs on ITS OWN rectification tables (host_setup.cpp, pinned to cv2 bit for bit in
+    # tests/test_product_tables_cv2.py); the checker gets the same tables so that both sides see identical inputs.
     for cam in (0, 1):
-        m1, m2, lut, mask = o.get_rectify_tables(cam)
-        g.set_rectify_tables(cam, m1, m2, lut, mask)
+        m1, m2, lut, mask = g.get_rectify_tables(cam)
+        o.set_rectify_tables(cam, m1, m2, lut, mask)
     return o, g
 
 
