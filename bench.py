@@ -319,7 +319,7 @@ def run_ours(args, rank, world, local_rank):
         nonlocal h2d, d2h
         res = None
         if len(tickets) >= max(1, args.pipeline_depth - 1):
-            m, res = g.results_end(tickets.pop(0))
+            m, res = g.results_end_view(tickets.pop(0))
             d2h += 64 + 64 + m.nbytes + m.size * 8
         for cam, side in ((0, "left"), (1, "right")):
             e = f[side]
@@ -339,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
         nonlocal d2h
         res = None
         while tickets:
-            m, res = g.results_end(tickets.pop(0))
+            m, res = g.results_end_view(tickets.pop(0))
             d2h += 64 + 64 + m.nbytes + m.size * 8
         return res
 

@@ -432,6 +432,19 @@ class Backend:
         keys = ["n_events", "n_seeds", "n_solved", "n_culled", "n_fusions", "bm_evals", "lm_evals", "map_size"]
         return out[: n.value], dict(zip(keys, [int(v) for v in ctr]))
 
+    def results_end_view(self, ticket):
+        """Zero-copy esvo_results_end: a numpy view of the slot's pinned landing buffer (valid until the slot's next results_begin)."""
+        ptr = C.c_void_p(); n = C.c_size_t(0); ctr = (C.c_uint64 * 8)()
+        self._call("results_end_view", [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)],
+                   int(ticket), C.byref(ptr), C.byref(n), ctr)
+        keys = ["n_events", "n_seeds", "n_solved", "n_culled", "n_fusions", "bm_evals", "lm_evals", "map_size"]
+        if n.value:
+            buf = (C.c_char * (n.value * DEPTH_POINT_DTYPE.itemsize)).from_address(ptr.value)
+            out = np.frombuffer(buf, dtype=DEPTH_POINT_DTYPE, count=n.value)
+        else:
+            out = np.zeros(0, DEPTH_POINT_DTYPE)
+        return out, dict(zip(keys, [int(v) for v in ctr]))
+
     def sync(self):
         self._call("sync", [])
 

@@ -46,10 +46,9 @@ int smooth_obs(Ctx* c) {
 int map_alloc_inputs(Ctx* c, size_t n_ev, size_t n_poses) {
   if (n_ev > c->ev_cap) {
     size_t cap = std::max<size_t>(n_ev, 1024);
-    void* olds[] = {c->d_ex, c->d_ey, c->d_et, c->bm.flag, c->bm.disp, c->bm.pose_idx, c->bm.cost, c->bm.xrect,
+    void* olds[] = {c->bm.flag, c->bm.disp, c->bm.pose_idx, c->bm.cost, c->bm.xrect,
                     c->d_seeds, c->lm_flag, c->lm_res, c->d_pts, c->lm_dbg};
     for (void* p : olds) if (p) cudaFree(p);
-    ESVO_CUDA_TRY(c, dmalloc(&c->d_ex, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_ey, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_et, cap));
     ESVO_CUDA_TRY(c, dmalloc(&c->bm.flag, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->bm.disp, cap));
     ESVO_CUDA_TRY(c, dmalloc(&c->bm.pose_idx, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->bm.cost, cap));
     ESVO_CUDA_TRY(c, dmalloc(&c->bm.xrect, 2 * cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_seeds, cap));
@@ -58,18 +57,44 @@ int map_alloc_inputs(Ctx* c, size_t n_ev, size_t n_poses) {
     ESVO_CUDA_TRY(c, dmalloc(&c->lm_dbg, 4 * cap));
     c->ev_cap = cap;
   }
-  if (n_poses > c->pose_cap) {
-    size_t cap = std::max<size_t>(n_poses, 256);
-    if (c->d_pose_t) cudaFree(c->d_pose_t);
-    if (c->d_poses) cudaFree(c->d_poses);
-    ESVO_CUDA_TRY(c, dmalloc(&c->d_pose_t, cap)); ESVO_CUDA_TRY(c, dmalloc(&c->d_poses, 16 * cap));
-    c->pose_cap = cap;
+  if (n_poses > c->pose_cap) c->pose_cap = std::max<size_t>(n_poses, 256);
+  const size_t need = c->ev_cap * 12 + c->pose_cap * 136 + 64;
+  if (need > c->in_bytes) {
+    if (c->ev_in_valid) { ESVO_CUDA_TRY(c, cudaEventSynchronize(c->ev_in)); c->ev_in_valid = false; }
+    if (c->d_in) { ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_in); }
+    if (c->h_in) cudaFreeHost(c->h_in);
+    ESVO_CUDA_TRY(c, dmalloc(&c->d_in, need));
+    ESVO_CUDA_TRY(c, cudaMallocHost((void**)&c->h_in, need));
+    if (!c->ev_in) ESVO_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+    c->in_bytes = need;
+    c->d_ex = c->d_ey = nullptr; c->d_et = c->d_pose_t = nullptr; c->d_poses = nullptr;
   }
   return ESVO_OK;
 }
 
-#define SLOT_FIELDS(X) X(obs_l) X(obs_r) X(obs_ls) X(obs_rs) X(d_T_left_world) X(ev_cap) X(pose_cap) X(n_ev) X(n_poses) \
-  X(d_ex) X(d_ey) X(d_et) X(d_pose_t) X(d_poses) X(bm) X(d_seeds) X(lm_flag) X(lm_res) X(lm_dbg) X(d_pts) X(d_counters) \
+// Host arrays -> the slot's packed device block with ONE H2D copy (layout: et | pose_t | poses | ex | ey).
+int stage_inputs_packed(Ctx* c, const uint16_t* ex, const uint16_t* ey, const int64_t* et, size_t n, const int64_t* pt,
+                        const double* poses, size_t np) {
+  int rc = map_alloc_inputs(c, n, np);
+  if (rc) return rc;
+  c->n_ev = n; c->n_poses = np;
+  if (c->ev_in_valid) ESVO_CUDA_TRY(c, cudaEventSynchronize(c->ev_in));   // the previous upload from this pinned mirror (long done)
+  const size_t o_et = 0, o_pt = o_et + n * 8, o_ps = o_pt + np * 8, o_ex = o_ps + np * 128, o_ey = o_ex + ((n * 2 + 7) & ~(size_t)7);
+  const size_t total = o_ey + n * 2;
+  if (n) { std::memcpy(c->h_in + o_et, et, n * 8); std::memcpy(c->h_in + o_ex, ex, n * 2); std::memcpy(c->h_in + o_ey, ey, n * 2); }
+  if (np) { std::memcpy(c->h_in + o_pt, pt, np * 8); std::memcpy(c->h_in + o_ps, poses, np * 128); }
+  c->d_et = (int64_t*)(c->d_in + o_et); c->d_pose_t = (int64_t*)(c->d_in + o_pt); c->d_poses = (double*)(c->d_in + o_ps);
+  c->d_ex = (uint16_t*)(c->d_in + o_ex); c->d_ey = (uint16_t*)(c->d_in + o_ey);
+  if (total) {
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_in, c->h_in, total, cudaMemcpyHostToDevice, c->stream));
+    ESVO_CUDA_TRY(c, cudaEventRecord(c->ev_in, c->stream));
+    c->ev_in_valid = true;
+  }
+  return ESVO_OK;
+}
+
+#define SLOT_FIELDS(X) X(obs_l) X(obs_r) X(obs_ls) X(obs_rs) X(ev_cap) X(pose_cap) X(n_ev) X(n_poses) \
+  X(d_ex) X(d_ey) X(d_et) X(d_pose_t) X(d_poses) X(d_in) X(h_in) X(in_bytes) X(ev_in) X(ev_in_valid) X(bm) X(d_seeds) X(lm_flag) X(lm_res) X(lm_dbg) X(d_pts) X(d_counters) \
   X(h_counters) X(h_pin) X(map)
 void slot_save(Ctx* c) {
   SlotBufs& s = c->slots[c->cur];
@@ -77,6 +102,7 @@ void slot_save(Ctx* c) {
   SLOT_FIELDS(X)
 #undef X
   std::memcpy(s.T_world_left, c->T_world_left, sizeof(s.T_world_left));
+  std::memcpy(s.T_left_world_inv, c->T_left_world_inv, sizeof(s.T_left_world_inv));
 }
 void slot_load(Ctx* c, int i) {
   SlotBufs& s = c->slots[i];
@@ -84,6 +110,7 @@ void slot_load(Ctx* c, int i) {
   SLOT_FIELDS(X)
 #undef X
   std::memcpy(c->T_world_left, s.T_world_left, sizeof(s.T_world_left));
+  std::memcpy(c->T_left_world_inv, s.T_left_world_inv, sizeof(s.T_left_world_inv));
   c->cur = i;
   c->stream = s.stream;
 }
@@ -95,7 +122,7 @@ int slot_alloc(Ctx* c, int i) {
   ESVO_CUDA_TRY(c, dmalloc(&s.obs_l, nimg)); ESVO_CUDA_TRY(c, dmalloc(&s.obs_r, nimg));
   ESVO_CUDA_TRY(c, dmalloc(&s.own_ls, nimg)); ESVO_CUDA_TRY(c, dmalloc(&s.own_rs, nimg));
   s.obs_ls = s.own_ls; s.obs_rs = s.own_rs;
-  ESVO_CUDA_TRY(c, dmalloc(&s.d_T_left_world, 16)); ESVO_CUDA_TRY(c, dmalloc(&s.d_counters, kCounters));
+  ESVO_CUDA_TRY(c, dmalloc(&s.d_counters, kCounters));
   ESVO_CUDA_TRY(c, cudaMallocHost((void**)&s.h_counters, kCounters * 8));
   ESVO_CUDA_TRY(c, cudaMallocHost((void**)&s.h_pin, 64 * 8));
   ESVO_CUDA_TRY(c, cudaMemset(s.d_counters, 0, kCounters * 8));
@@ -121,6 +148,16 @@ int drain(Ctx* c) {
     if (c->slots[i].stream) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->slots[i].stream));
   }
   if (c->s_copy) ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->s_copy));
+  // Everything pushed so far has landed: refresh the host's view of the newest stamp from the device scalar, so that
+  // builds after device-resident pushes can take the short path again (ts.cu: maybe_general)
+  for (int k = 0; k < 2; ++k) {
+    TsState& t = c->ts[k];
+    if (!t.host_knows && !t.unordered && t.max_t) {
+      long long v = 0;
+      ESVO_CUDA_TRY(c, cudaMemcpy(&v, t.max_t, 8, cudaMemcpyDeviceToHost));
+      t.host_max_t = v; t.host_knows = true;
+    }
+  }
   return ESVO_OK;
 }
 
@@ -149,19 +186,7 @@ static void rigid_inverse(const double* T, double* I) {
 
 static int stage_mapping(Ctx* c, const uint16_t* ex, const uint16_t* ey, const int64_t* et, size_t n,
                          const int64_t* pt, const double* poses, size_t np) {
-  int rc = map_alloc_inputs(c, n, np);
-  if (rc) return rc;
-  c->n_ev = n; c->n_poses = np;
-  if (n) {
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ex, ex, n * 2, cudaMemcpyHostToDevice, c->stream));
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ey, ey, n * 2, cudaMemcpyHostToDevice, c->stream));
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_et, et, n * 8, cudaMemcpyHostToDevice, c->stream));
-  }
-  if (np) {
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_pose_t, pt, np * 8, cudaMemcpyHostToDevice, c->stream));
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_poses, poses, np * 16 * 8, cudaMemcpyHostToDevice, c->stream));
-  }
-  return ESVO_OK;
+  return stage_inputs_packed(c, ex, ey, et, n, pt, poses, np);
 }
 
 static int fetch_counters(Ctx* c) {
@@ -225,6 +250,11 @@ ESVO_API esvo_ctx* esvo_create(int device, const esvo_calib* left, const esvo_ca
   if (p->patch_size_x * p->patch_size_y > kMaxPatch || p->patch_size_x < 1 || p->patch_size_y < 1 ||
       !(p->patch_size_x & 1) || !(p->patch_size_y & 1))
     return fail(ESVO_ERR_UNSUPPORTED);
+  // The closed-form cam2World / propagation (lm.cu, fuse.cu) assume a canonical rectified projection
+  // P = [fx 0 cx tx; 0 fy cy ty; 0 0 1 0] (every shipped calibration); the reference's 4x4 inverse is more general.
+  for (const esvo_calib* cal : {left, right})
+    if (cal->P[1] != 0 || cal->P[4] != 0 || cal->P[8] != 0 || cal->P[9] != 0 || cal->P[10] != 1 || cal->P[11] != 0)
+      return fail(ESVO_ERR_UNSUPPORTED);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return fail(ESVO_ERR_NO_DEVICE);
   if (cudaSetDevice(device) != cudaSuccess) return fail(ESVO_ERR_NO_DEVICE);
@@ -281,12 +311,13 @@ ESVO_API void esvo_destroy(esvo_ctx* c) {
   if (c->d_mask) cudaFree(c->d_mask);
   for (int i = 0; i < kMaxSlots; ++i) {
     SlotBufs& s = c->slots[i];
-    void* ps[] = {s.obs_l, s.obs_r, s.own_ls, s.own_rs, s.d_T_left_world, s.d_counters, s.d_ex, s.d_ey, s.d_et, s.d_pose_t,
-                  s.d_poses, s.bm.flag, s.bm.disp, s.bm.pose_idx, s.bm.cost, s.bm.xrect, s.d_seeds, s.lm_flag, s.lm_res,
+    void* ps[] = {s.obs_l, s.obs_r, s.own_ls, s.own_rs, s.d_counters, s.d_in, s.bm.flag, s.bm.disp, s.bm.pose_idx, s.bm.cost, s.bm.xrect, s.d_seeds, s.lm_flag, s.lm_res,
                   s.d_pts, s.lm_dbg};
     for (void* p : ps) if (p) cudaFree(p);
     if (s.h_counters) cudaFreeHost(s.h_counters);
     if (s.h_pin) cudaFreeHost(s.h_pin);
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.ev_in) cudaEventDestroy(s.ev_in);
     if (s.ev_obs) cudaEventDestroy(s.ev_obs);
     if (s.ev_free) cudaEventDestroy(s.ev_free);
     if (s.ev_pts) cudaEventDestroy(s.ev_pts);
@@ -320,7 +351,7 @@ ESVO_API int esvo_set_rectify_tables(esvo_ctx* c, int cam, const float* m1, cons
   if (lut) c->cam[cam].lut.assign(lut, lut + 2 * n);
   c->tables_version++;
   if (mask) c->cam[cam].mask.assign(mask, mask + n);
-  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  { int rc0 = drain(c); if (rc0) return rc0; }   // kernels of other pipeline slots / the TS streams may still read the tables
   return upload_tables(c);
 }
 ESVO_API int esvo_get_rectify_tables(esvo_ctx* c, int cam, float* m1, float* m2, double* lut, uint8_t* mask) {
@@ -426,9 +457,7 @@ ESVO_API int esvo_set_ts_pair(esvo_ctx* c, const uint8_t* l, const uint8_t* r, c
     if (c->obs_r != c->ts[1].last_img) ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_r, c->ts[1].last_img, nimg, cudaMemcpyDeviceToDevice, c->stream));
   }
   std::memcpy(c->T_world_left, T, sizeof(c->T_world_left));
-  double Ti[16];
-  rigid_inverse(T, Ti);
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_T_left_world, Ti, sizeof(Ti), cudaMemcpyHostToDevice, c->stream));
+  rigid_inverse(T, c->T_left_world_inv);
   // Until createMatchProblem smooths it, the observation the solver reads is the raw pair.
   if (!c->prm.smooth_time_surface) { c->obs_ls = c->obs_l; c->obs_rs = c->obs_r; }
   else {
@@ -436,7 +465,7 @@ ESVO_API int esvo_set_ts_pair(esvo_ctx* c, const uint8_t* l, const uint8_t* r, c
     ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->obs_rs, c->obs_r, nimg, cudaMemcpyDeviceToDevice, c->stream));
   }
   ESVO_CUDA_TRY(c, cudaEventRecord(c->slots[c->cur].ev_obs, c->stream));
-  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // Ti and the caller's images are host stack/heap
+  ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // the caller's images are host memory
   c->obs_set = true;
   return ESVO_OK;
 }
@@ -470,9 +499,7 @@ ESVO_API int esvo_set_ts_pair_dev(esvo_ctx* c, const double T[16]) {
   }
   if (!c->prm.smooth_time_surface) { c->obs_ls = c->obs_l; c->obs_rs = c->obs_r; }   // otherwise smooth_obs() fills obs_ls/obs_rs
   std::memcpy(c->T_world_left, T, sizeof(c->T_world_left));
-  // pinned block of this slot: its previous upload finished long ago (same stream, S frames back)
-  rigid_inverse(T, c->h_pin);
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_T_left_world, c->h_pin, 128, cudaMemcpyHostToDevice, c->stream));
+  rigid_inverse(T, c->T_left_world_inv);     // travels to the LM kernel by value: no upload, nothing pinned to guard
   c->obs_set = true;
   return ESVO_OK;
 }

@@ -1,6 +1,7 @@
 // esvo_b200 product code -- C ABI, part 2: culling, fusion, map and whole-frame mapping entry points.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -104,15 +105,19 @@ static int run_mapping_frame(Ctx* c) {
       c->win.erase(c->win.begin());
     }
   }
+  // The window holds vectors written by the point-ordering kernels of the previous frames, which run on other slots'
+  // streams and may finish later than ours (LM tails).  Chain the "points ready" events: ev_pts of frame k is recorded
+  // behind a wait on ev_pts of frame k-1, so waiting on one event covers every older vector (one wait instead of depth-1).
+  if (c->depth > 1 && c->frame_no >= 1) {
+    SlotBufs& prev = c->slots[(int)((c->frame_no - 1) % (uint64_t)c->depth)];
+    if (prev.ev_pts_valid) ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, prev.ev_pts, 0));
+  }
   ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_pts, c->stream));
   sl.ev_pts_valid = true;
-  // the window holds vectors written by the point-ordering kernels of the previous frames, which run on
-  // other slots' streams and may finish later than ours (LM tails): wait for them (not for their fusions)
-  for (int i = 0; i < c->depth; ++i)
-    if (i != c->cur && c->slots[i].ev_pts_valid) ESVO_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->slots[i].ev_pts, 0));
+  static const int dbg_skip_fuse = getenv("ESVO_DBG_SKIP_FUSE") ? atoi(getenv("ESVO_DBG_SKIP_FUSE")) : 0;   // experiment only
+  if (dbg_skip_fuse) { ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_fuse, c->stream)); sl.ev_fuse_valid = true; c->frame_no++; return ESVO_OK; }
   pe = c->prof_begin(5);
   if ((rc = fuse_reset_map(c, c->T_world_left))) return rc;               // :268-272 fresh DepthFrame at the obs pose
-  if ((rc = fuse_zero_fusion_counter(c))) return rc;
   {  // size the staging area once for a full window so that steady-state frames never reallocate
     size_t tot = 0, mx = 0;
     for (auto& w : c->win) { tot += w.cap; mx = std::max(mx, w.cap); }
@@ -120,16 +125,22 @@ static int run_mapping_frame(Ctx* c) {
     if ((rc = fuse_reserve(c, tot))) return rc;
   }
   {                                                                       // :372-377 newest first
-    std::vector<Ctx::WinFrame> order(c->win.rbegin(), c->win.rend());
-    if ((rc = fuse_window(c, order.data(), (int)order.size(), p.fusion_radius))) return rc;
+    Ctx::WinFrame order[64];
+    std::vector<Ctx::WinFrame> big;
+    const Ctx::WinFrame* ord = order;
+    const size_t nw = c->win.size();
+    if (nw <= 64) for (size_t i = 0; i < nw; ++i) order[i] = c->win[nw - 1 - i];
+    else { big.assign(c->win.rbegin(), c->win.rend()); ord = big.data(); }
+    if ((rc = fuse_window(c, ord, (int)nw, p.fusion_radius))) return rc;
   }
-  if ((rc = fuse_finish(c))) return rc;
-  if (c->win.size() >= (size_t)p.max_num_fusion_frames)                   // :385-386
-    if ((rc = map_clean(c, p.stdvar_vis_threshold * p.stdvar_vis_threshold, p.age_vis_threshold, p.invdepth_max_range,
-                        p.invdepth_min_range)))
-      return rc;
-  if (p.regularization && (rc = map_regularize(c))) return rc;            // :390-395
-  rc = map_count(c);
+  {
+    // :385-386 SmartGrid::clean once the window is full -- applied by the fold itself to the pixels it finishes
+    const double clean4[4] = {p.stdvar_vis_threshold * p.stdvar_vis_threshold, p.age_vis_threshold, p.invdepth_max_range, p.invdepth_min_range};
+    const bool do_clean = c->win.size() >= (size_t)p.max_num_fusion_frames;
+    if ((rc = fuse_finish(c, false, do_clean ? clean4 : nullptr))) return rc;
+  }
+  if (p.regularization) rc = map_regularize(c, /*count=*/true);           // :390-395, + element count
+  else rc = map_count(c);
   c->prof_end(pe);
   ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_fuse, c->stream));
   sl.ev_fuse_valid = true;
@@ -257,7 +268,7 @@ ESVO_API int esvo_init_from_disparity(esvo_ctx* c, const int16_t* disp16, const 
   if (n && ce == cudaSuccess) ce = cudaMemcpyAsync(d_y, ey, n * 2, cudaMemcpyHostToDevice, c->stream);
   if (ce != cudaSuccess) { cleanup(); c->win_pool.push_back(f); c->set_error(cudaGetErrorString(ce)); return ESVO_ERR_CUDA; }
   unsigned long long cnt = 0;
-  if ((rc = fuse_reset_map(c, T)) == ESVO_OK && (rc = sgm_points(c, d_disp, d_x, d_y, n, map_T_world_frame_dev(c), f.pts, f.cnt)) == ESVO_OK) {
+  if ((rc = fuse_reset_map(c, T)) == ESVO_OK && (rc = sgm_points(c, d_disp, d_x, d_y, n, f.pts, f.cnt)) == ESVO_OK) {
     if (cudaMemcpyAsync(&cnt, f.cnt, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
       rc = ESVO_ERR_CUDA;
   }
@@ -308,20 +319,10 @@ ESVO_API int esvo_stage_mapping_inputs(esvo_ctx* c, const uint16_t* ex, const ui
   CHECK_CTX(c);
   if (n && (!ex || !ey || !et)) return ESVO_ERR_INVALID_ARG;
   if (np && (!pt || !poses)) return ESVO_ERR_INVALID_ARG;
-  int rc = map_alloc_inputs(c, n, np);
-  if (rc) return rc;
-  c->n_ev = n; c->n_poses = np;
-  if (n) {
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ex, ex, n * 2, cudaMemcpyHostToDevice, c->stream));
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ey, ey, n * 2, cudaMemcpyHostToDevice, c->stream));
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_et, et, n * 8, cudaMemcpyHostToDevice, c->stream));
-  }
-  if (np) {
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_pose_t, pt, np * 8, cudaMemcpyHostToDevice, c->stream));
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_poses, poses, np * 16 * 8, cudaMemcpyHostToDevice, c->stream));
-  }
-  return ESVO_OK;
+  return stage_inputs_packed(c, ex, ey, et, n, pt, poses, np);    // the caller's arrays are free again on return
 }
+// Device-resident inputs are used IN PLACE (no copy): they must stay valid and unchanged until the frame has been
+// collected (esvo_results_end) or the ctx synchronised.
 ESVO_API int esvo_stage_mapping_inputs_dev(esvo_ctx* c, const uint16_t* ex, const uint16_t* ey, const int64_t* et, size_t n,
                                            const int64_t* pt, const double* poses, size_t np) {
   CHECK_CTX(c);
@@ -330,15 +331,8 @@ ESVO_API int esvo_stage_mapping_inputs_dev(esvo_ctx* c, const uint16_t* ex, cons
   int rc = map_alloc_inputs(c, n, np);
   if (rc) return rc;
   c->n_ev = n; c->n_poses = np;
-  if (n) {
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ex, ex, n * 2, cudaMemcpyDeviceToDevice, c->stream));
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_ey, ey, n * 2, cudaMemcpyDeviceToDevice, c->stream));
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_et, et, n * 8, cudaMemcpyDeviceToDevice, c->stream));
-  }
-  if (np) {
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_pose_t, pt, np * 8, cudaMemcpyDeviceToDevice, c->stream));
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_poses, poses, np * 16 * 8, cudaMemcpyDeviceToDevice, c->stream));
-  }
+  c->d_ex = const_cast<uint16_t*>(ex); c->d_ey = const_cast<uint16_t*>(ey); c->d_et = const_cast<int64_t*>(et);
+  c->d_pose_t = const_cast<int64_t*>(pt); c->d_poses = const_cast<double*>(poses);
   return ESVO_OK;
 }
 // ---- asynchronous result hand-off for pipelined operation ----
@@ -366,9 +360,8 @@ ESVO_API int esvo_results_begin(esvo_ctx* c, int64_t* ticket_out) {
   if (!c->s_copy) ESVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
   {
     // right behind this frame's fusion on the slot's own stream
-    int rc = map_gather_async(c, sl.d_dl, sl.d_dl_keys, sl.d_dlscal, sl.h_dlscal, (esvo_depth_point*)sl.h_dl);
+    int rc = map_gather_async(c, sl.d_dl, sl.d_dl_keys, sl.d_dlscal, sl.h_dlscal, (esvo_depth_point*)sl.h_dl, sl.h_counters);
     if (rc) return rc;
-    ESVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_counters, sl.d_counters, kCounters * 8, cudaMemcpyDeviceToHost, c->stream));
     ESVO_CUDA_TRY(c, cudaEventRecord(sl.ev_dl, c->stream));
   }
   sl.dl_ticket = (int64_t)c->frame_no - 1;
@@ -378,8 +371,10 @@ ESVO_API int esvo_results_begin(esvo_ctx* c, int64_t* ticket_out) {
 ESVO_API int esvo_results_end(esvo_ctx* c, int64_t ticket, esvo_depth_point* out, size_t* n, uint64_t counters[8]) {
   CHECK_CTX(c);
   if (!n || ticket < 0) return ESVO_ERR_INVALID_ARG;
-  SlotBufs& sl = c->slots[(int)(ticket % c->depth)];
-  if (sl.dl_ticket != ticket) { c->set_error("esvo_results_end: unknown ticket"); return ESVO_ERR_STATE; }
+  int si = -1;
+  for (int i = 0; i < kMaxSlots; ++i) if (c->slots[i].dl_ticket == ticket) { si = i; break; }   // slots need not rotate (host esvo_set_ts_pair keeps one)
+  if (si < 0) { c->set_error("esvo_results_end: unknown ticket"); return ESVO_ERR_STATE; }
+  SlotBufs& sl = c->slots[si];
   ESVO_CUDA_TRY(c, cudaEventSynchronize(sl.ev_dl));
   const size_t cnt = (size_t)sl.h_dlscal[1];
   if (counters) {
@@ -387,8 +382,28 @@ ESVO_API int esvo_results_end(esvo_ctx* c, int64_t ticket, esvo_depth_point* out
     counters[4] = sl.h_dlscal[4]; counters[5] = sl.h_counters[5]; counters[6] = sl.h_counters[6]; counters[7] = sl.h_dlscal[6];
   }
   if (cnt > *n) { *n = cnt; return ESVO_ERR_CAPACITY; }
+  if (cnt && !out) return ESVO_ERR_INVALID_ARG;
   std::memcpy(out, sl.h_dl, cnt * sizeof(esvo_depth_point));   // already in SmartGrid list order (creation sequence)
   *n = cnt;
+  sl.dl_ticket = -1;
+  return ESVO_OK;
+}
+// Zero-copy form: *out points into the slot's pinned landing buffer (written by the gather kernel over PCIe); valid until the
+// slot issues its next esvo_results_begin.
+ESVO_API int esvo_results_end_view(esvo_ctx* c, int64_t ticket, const esvo_depth_point** out, size_t* n, uint64_t counters[8]) {
+  CHECK_CTX(c);
+  if (!n || !out || ticket < 0) return ESVO_ERR_INVALID_ARG;
+  int si = -1;
+  for (int i = 0; i < kMaxSlots; ++i) if (c->slots[i].dl_ticket == ticket) { si = i; break; }
+  if (si < 0) { c->set_error("esvo_results_end_view: unknown ticket"); return ESVO_ERR_STATE; }
+  SlotBufs& sl = c->slots[si];
+  ESVO_CUDA_TRY(c, cudaEventSynchronize(sl.ev_dl));
+  if (counters) {
+    counters[0] = sl.n_ev; counters[1] = sl.h_counters[1]; counters[2] = sl.h_counters[2]; counters[3] = sl.h_counters[3];
+    counters[4] = sl.h_dlscal[4]; counters[5] = sl.h_counters[5]; counters[6] = sl.h_counters[6]; counters[7] = sl.h_dlscal[6];
+  }
+  *out = (const esvo_depth_point*)sl.h_dl;
+  *n = (size_t)sl.h_dlscal[1];
   sl.dl_ticket = -1;
   return ESVO_OK;
 }

@@ -41,16 +41,20 @@ struct MapState {
   size_t prop_cap = 0, staged = 0;
   int32_t* head = nullptr;       // per pixel, -1 = empty
   int32_t* next = nullptr;       // per contribution (9 per staged point)
+  int32_t* active = nullptr;     // pixels touched since the last reset, in first-touch order (count in d_scal[3])
+  uint32_t* cbits = nullptr;     // one bit per contribution id: "this contribution created its pixel's element" (ordered hand-off)
+  uint32_t* cprefix = nullptr;   // exclusive popcount prefix per word of cbits
+  size_t cbits_words = 0;
+  int folds = 0;                 // folds since the last reset
+  size_t fold_words = 0;         // bitmap words covering the ids of the first fold after the reset
+  bool list_valid = false;       // every existing pixel is in `active` (true from a reset until a kernel that ignores the list runs)
   unsigned long long seq_base = 0;
   double T_world_frame[16];
   double T_frame_world[16];
-  double* d_T_frame_world = nullptr;
   esvo_depth_point* d_dl = nullptr;      // download staging
   unsigned long long* d_dl_keys = nullptr;
-  unsigned long long* d_scal = nullptr;  // [0] n_fusions, [1] download count
+  unsigned long long* d_scal = nullptr;  // [0] n_fusions, [1] download count, [2] map size, [3] number of active pixels
   unsigned long long* h_scal = nullptr;
-  double* h_T_ring = nullptr;            // pinned, 8 x 32 doubles: frame poses uploaded without a host sync
-  unsigned ring_idx = 0;
 };
 
 template <class T> static cudaError_t dm(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
@@ -72,8 +76,10 @@ struct FrameSet {
   int off[FS_MAX + 1];                     // thread / staging offsets (prefix sums of cap)
   int nframes;
 };
-__global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, const double* __restrict__ T_frame_world,
-                                  int radius, int stage_off, PropSoA P, int32_t* head, int32_t* next) {
+struct Pose16 { double m[16]; };
+__global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, Pose16 Tfw, int radius, int stage_off, PropSoA P, int32_t* head,
+                                  int32_t* next, int32_t* active, unsigned long long* scal) {
+  const double* T_frame_world = Tfw.m;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= fs.off[fs.nframes]) return;
   int f = 0;
@@ -128,19 +134,30 @@ __global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, const double* __res
       const int r = row + dy, c = col + dx;
       if (r < 0 || c < 0 || r >= dc.H || c >= dc.W) continue;
       const int cid = sid * 9 + i;
-      next[cid] = atomicExch(&head[(size_t)r * dc.W + c], cid);
+      const int pix = r * dc.W + c;
+      const int old = atomicExch(&head[pix], cid);
+      next[cid] = old;
+      // first contribution to this pixel since its list was last folded: the pixel joins the active list (a pixel that
+      // is folded twice between two resets is listed twice; the list kernels tolerate that, see map_*_list)
+      if (old < 0) active[atomicAdd(&scal[3], 1ULL)] = pix;
     }
 }
 
 // ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
 // NAIVE = DepthFusion::naive_propagation (:232-288): same ordered replay, but nearest-wins instead of fusion.
+struct CleanArgs { int enable; double var_thr, age_thr, rmax, rmin; };
+// One thread per ACTIVE pixel (dense: the list holds exactly the pixels with a non-empty contribution list), so a warp
+// carries 32 replays instead of the 1-3 a thread-per-image-pixel launch would (the fold's cost in the frame pipeline is
+// warp-slot time, not instructions: profiles/r2_*).
 template <bool NAIVE>
 __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* head, const int32_t* __restrict__ next,
-                                 unsigned long long seq_base, unsigned long long* scal) {
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= dc.W * dc.H) return;
+                                 const int32_t* __restrict__ active, unsigned long long seq_base, unsigned long long* scal,
+                                 uint32_t* cbits, CleanArgs clean) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((unsigned long long)t >= scal[3]) return;
+  const int pix = active[t];
   int h = head[pix];
-  if (h < 0) return;
+  if (h < 0) return;               // listed twice: the first copy folded it
   head[pix] = -1;
   // The list is in reverse insertion order of the atomics, not in sequence order: collect and sort.
   constexpr int CAP = 192;
@@ -197,7 +214,12 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
       compat = diff < r.sd2 || diff < sdm;
     }
     if (compat) {  // case 2.1 (:162-177)
-      if (dc.lsnorm == ESVO_LSNORM_L2) {
+      if (!(rho > -1e-6)) {
+        // DepthPoint::update / update_studentT take their "new point" branch for a map point that carries no valid inverse
+        // depth (DepthPoint.cpp:158-163,181-187; e.g. one marked -1 by the regularisation): overwrite, no inner age_++
+        rho = prho; var = pvar; s2 = ps2; nu = pnu;
+        if (dc.lsnorm == ESVO_LSNORM_L2 && var < 1e-6) var = 1e-6;
+      } else if (dc.lsnorm == ESVO_LSNORM_L2) {
         const double t = rho;
         rho = (var * prho + pvar * t) / (var + pvar);
         const double tv = var;
@@ -263,6 +285,12 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
     }
   }
   if (pc_pending) cam2world_f(dc, x0, x1, pc_rho, pc0, pc1, pc2);
+  // SmartGrid::clean (:222-243) right behind the fusion of the whole window (esvo_Mapping.cpp:385-386): the thread holds the
+  // pixel's final state, so the predicate is applied here instead of in a pass over the image
+  if (clean.enable && ex && !(rho > -1e-6 && (double)age >= clean.age_thr && var <= clean.var_thr && rho <= clean.rmax && rho >= clean.rmin))
+    ex = false;
+  // creator bit of the surviving element: rank in the element list = number of set bits below it (map_gather_list_kernel)
+  if (ex && cbits && fkey >= seq_base) { const unsigned long long cc = fkey - seq_base; atomicOr(&cbits[cc >> 5], 1u << (cc & 31)); }
   M.exists[pix] = ex ? 1 : 0;
   M.rho[pix] = rho; M.s2[pix] = s2; M.nu[pix] = nu; M.var[pix] = var; M.res[pix] = res; M.x0[pix] = x0; M.x1[pix] = x1;
   M.pc0[pix] = pc0; M.pc1[pix] = pc1; M.pc2[pix] = pc2; M.age[pix] = age; M.row[pix] = erow; M.col[pix] = ecol;
@@ -280,9 +308,14 @@ __global__ void map_clean_kernel(int npix, MapSoA M, double var_thr, double age_
 }
 
 // ---- DepthRegularization::apply ----
-__global__ void map_regularize_kernel(DevConsts dc, MapSoA M, int radius, int min_nb, int min_close) {
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= dc.W * dc.H) return;
+// LIST: one thread per active pixel (valid while every existing pixel is in the list exactly once: one fold since the reset)
+template <bool LIST>
+__global__ void map_regularize_kernel(DevConsts dc, MapSoA M, int radius, int min_nb, int min_close, const int32_t* __restrict__ active,
+                                      const unsigned long long* __restrict__ scal) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int pix = t;
+  if (LIST) { if ((unsigned long long)t >= scal[3]) return; pix = active[t]; }
+  else if (pix >= dc.W * dc.H) return;
   if (!M.exists[pix]) return;
   const double rho = M.rho[pix];
   M.rho_tmp[pix] = rho;
@@ -342,10 +375,82 @@ __global__ void map_regularize_commit_kernel(int npix, MapSoA M) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix < npix && M.exists[pix]) M.rho[pix] = M.rho_tmp[pix];
 }
+// list form of commit (+ the element count of map_count_kernel): scal[2] += number of existing pixels
+__global__ void map_commit_count_list_kernel(MapSoA M, int commit, const int32_t* __restrict__ active, unsigned long long* scal) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = 0;
+  if ((unsigned long long)t < scal[3]) {
+    const int pix = active[t];
+    e = M.exists[pix] ? 1 : 0;
+    if (e && commit) M.rho[pix] = M.rho_tmp[pix];
+  }
+  const int s = warp_sum_i(e);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(&scal[2], (unsigned long long)s);
+}
+// ---- ordered hand-off without sorting (one fold since the reset): the element list order is the order of the creating
+// contribution ids; fuse_fold_kernel left one bit per surviving creator.  (1) exclusive popcount prefix per bitmap word
+// (single block, a few thousand words), (2) every existing active pixel writes its element at position
+// rank = prefix[word] + popc(bits below) -- straight into the (pinned, device-mapped) destination.
+__device__ int block_excl_scan(int v, int* s_warp, int& total);
+__global__ void __launch_bounds__(1024) map_cbits_prefix_kernel(const uint32_t* __restrict__ bits, uint32_t* __restrict__ prefix, int nwords,
+                                                                unsigned long long* scal, unsigned long long* h_scal8,
+                                                                const uint64_t* __restrict__ d_counters, uint64_t* h_counters) {
+  __shared__ int s_warp[33];
+  const int per = (nwords + 1023) / 1024;
+  const int w0 = threadIdx.x * per, w1 = min(nwords, w0 + per);
+  int cnt = 0;
+  for (int w = w0; w < w1; ++w) cnt += __popc(bits[w]);
+  int total;
+  int run = block_excl_scan(cnt, s_warp, total);
+  for (int w = w0; w < w1; ++w) { prefix[w] = (uint32_t)run; run += __popc(bits[w]); }
+  if (threadIdx.x == 0) {
+    scal[1] = (unsigned long long)total;
+    if (h_scal8) { h_scal8[1] = (unsigned long long)total; h_scal8[4] = scal[0]; h_scal8[6] = scal[2]; }   // count, n_fusions, map size
+  }
+  if (h_counters && threadIdx.x < kCounters) h_counters[threadIdx.x] = d_counters[threadIdx.x];
+}
+__global__ void map_gather_list_kernel(MapSoA M, Pose16 Twf, const int32_t* __restrict__ active, const unsigned long long* __restrict__ scal,
+                                       const uint32_t* __restrict__ bits, const uint32_t* __restrict__ prefix, esvo_depth_point* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = (unsigned long long)t < scal[3];
+  const int pix = in ? active[t] : 0;
+  const bool ex = in && M.exists[pix];
+  unsigned rank = 0;
+  if (ex) { const unsigned long long c = M.first_key[pix]; rank = prefix[c >> 5] + __popc(bits[c >> 5] & ((1u << (c & 31)) - 1u)); }
+  // warp-cooperative element writes (28 x 8-byte words each): lane w moves word w of one element at a time
+  constexpr int WORDS = sizeof(esvo_depth_point) / 8;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned exmask = __ballot_sync(0xffffffffu, ex);
+  for (unsigned e = 0; e < 32; ++e) {
+    if (!((exmask >> e) & 1u)) continue;
+    const unsigned r = __shfl_sync(0xffffffffu, rank, e);
+    const int q = __shfl_sync(0xffffffffu, pix, e);
+    if (lane < WORDS) {
+      unsigned long long v;
+      switch (lane) {
+        case 0: { const unsigned long long lo = (unsigned)M.row[q], hi = (unsigned)M.col[q]; v = lo | (hi << 32); break; }
+        case 1: v = __double_as_longlong(M.x0[q]); break;
+        case 2: v = __double_as_longlong(M.x1[q]); break;
+        case 3: v = __double_as_longlong(M.rho[q]); break;
+        case 4: v = __double_as_longlong(M.s2[q]); break;
+        case 5: v = __double_as_longlong(M.nu[q]); break;
+        case 6: v = __double_as_longlong(M.var[q]); break;
+        case 7: v = __double_as_longlong(M.res[q]); break;
+        case 8: v = (unsigned long long)M.age[q]; break;
+        case 9: v = __double_as_longlong(M.pc0[q]); break;
+        case 10: v = __double_as_longlong(M.pc1[q]); break;
+        case 11: v = __double_as_longlong(M.pc2[q]); break;
+        default: v = __double_as_longlong(Twf.m[lane - 12]); break;
+      }
+      reinterpret_cast<unsigned long long*>(out + r)[lane] = v;
+    }
+  }
+}
 
 // ---- download: compact existing pixels (unordered) with their creation keys ----
-__global__ void map_gather_kernel(DevConsts dc, MapSoA M, const double* __restrict__ Twf, esvo_depth_point* out,
+__global__ void map_gather_kernel(DevConsts dc, MapSoA M, Pose16 TwfP, esvo_depth_point* out,
                                   unsigned long long* keys, unsigned long long* scal) {
+  const double* Twf = TwfP.m;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= dc.W * dc.H || !M.exists[pix]) return;
   const unsigned long long pos = atomicAdd(&scal[1], 1ULL);
@@ -440,9 +545,10 @@ __device__ void cam2world_general(const DevConsts& dc, double x, double y, doubl
 }
 __global__ void __launch_bounds__(1024) sgm_points_kernel(DevConsts dc, const int16_t* __restrict__ disp16,
                                                           const uint16_t* __restrict__ ex, const uint16_t* __restrict__ ey, int n,
-                                                          const double* __restrict__ lut, const double* __restrict__ T_world_cam,
+                                                          const double* __restrict__ lut, Pose16 TwcP,
                                                           double rho_min, double rho_max, long long age0, esvo_depth_point* out,
                                                           unsigned long long* out_cnt) {
+  const double* T_world_cam = TwcP.m;
   __shared__ int s_warp[33];
   int running = 0;
   for (int k0 = 0; k0 < n; k0 += blockDim.x) {
@@ -481,11 +587,11 @@ __global__ void __launch_bounds__(1024) sgm_points_kernel(DevConsts dc, const in
   }
   if (threadIdx.x == 0) *out_cnt = (unsigned long long)running;
 }
-// device copy of the current map's T_world_frame (uploaded by fuse_reset_map, stream-ordered)
-const double* map_T_world_frame_dev(Ctx* c) { return c->map->d_T_frame_world + 16; }
-int sgm_points(Ctx* c, const int16_t* d_disp, const uint16_t* d_ex, const uint16_t* d_ey, size_t n, const double* d_T_world_cam,
-               esvo_depth_point* out, unsigned long long* out_cnt) {
-  sgm_points_kernel<<<1, 1024, 0, c->stream>>>(c->dc, d_disp, d_ex, d_ey, (int)n, c->d_lut, d_T_world_cam, c->prm.invdepth_min_range,
+// T_world_cam = pose of the current map (host copy kept by fuse_reset_map), passed by value
+int sgm_points(Ctx* c, const int16_t* d_disp, const uint16_t* d_ex, const uint16_t* d_ey, size_t n, esvo_depth_point* out,
+               unsigned long long* out_cnt) {
+  Pose16 Twc; std::memcpy(Twc.m, c->map->T_world_frame, 128);
+  sgm_points_kernel<<<1, 1024, 0, c->stream>>>(c->dc, d_disp, d_ex, d_ey, (int)n, c->d_lut, Twc, c->prm.invdepth_min_range,
                                                c->prm.invdepth_max_range, (long long)c->prm.age_vis_threshold, out, out_cnt);
   c->launches += 1;
   ESVO_CUDA_TRY(c, cudaGetLastError());
@@ -504,13 +610,16 @@ static int prop_reserve(Ctx* c, size_t need) {
   if (ms->staged) { c->set_error("internal: staging buffer grown while points are staged"); return ESVO_ERR_STATE; }
   size_t cap = std::max<size_t>(need, 65536);
   PropSoA& P = ms->p;
-  void* olds[] = {P.hot, P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col, ms->next};
+  void* olds[] = {P.hot, P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col, ms->next,
+                  ms->cbits, ms->cprefix};
   for (void* p : olds) if (p) cudaFree(p);
   ESVO_CUDA_TRY(c, dm(&P.ok, cap)); ESVO_CUDA_TRY(c, dm(&P.hot, cap));
   double** ds[] = {&P.rho, &P.s2, &P.nu, &P.var, &P.res, &P.x0, &P.x1, &P.pc0, &P.pc1, &P.pc2};
   for (double** d : ds) ESVO_CUDA_TRY(c, dm(d, cap));
   ESVO_CUDA_TRY(c, dm(&P.age, cap)); ESVO_CUDA_TRY(c, dm(&P.row, cap)); ESVO_CUDA_TRY(c, dm(&P.col, cap));
   ESVO_CUDA_TRY(c, dm(&ms->next, cap * 9));
+  ms->cbits_words = (cap * 9 + 31) / 32;
+  ESVO_CUDA_TRY(c, dm(&ms->cbits, ms->cbits_words)); ESVO_CUDA_TRY(c, dm(&ms->cprefix, ms->cbits_words));
   ms->prop_cap = cap;
   return ESVO_OK;
 }
@@ -527,17 +636,15 @@ int fuse_alloc(Ctx* c) {
   ESVO_CUDA_TRY(c, dm(&M.age, npix)); ESVO_CUDA_TRY(c, dm(&M.row, npix)); ESVO_CUDA_TRY(c, dm(&M.col, npix));
   ESVO_CUDA_TRY(c, dm(&M.first_key, npix));
   ESVO_CUDA_TRY(c, dm(&ms->head, npix));
-  ESVO_CUDA_TRY(c, dm(&ms->d_T_frame_world, 32));
+  ESVO_CUDA_TRY(c, dm(&ms->active, npix));
   ESVO_CUDA_TRY(c, dm(&ms->d_dl, npix)); ESVO_CUDA_TRY(c, dm(&ms->d_dl_keys, npix));
   ESVO_CUDA_TRY(c, dm(&ms->d_scal, 4));
   ESVO_CUDA_TRY(c, cudaMallocHost((void**)&ms->h_scal, 4 * 8));
-  ESVO_CUDA_TRY(c, cudaMallocHost((void**)&ms->h_T_ring, 8 * 32 * 8));
   ESVO_CUDA_TRY(c, cudaMemset(M.exists, 0, npix));
-  ESVO_CUDA_TRY(c, cudaMemset(ms->head, 0xff, npix * 4));
+  ESVO_CUDA_TRY(c, cudaMemset(ms->head, 0xff, npix * 4));   // invariant: every fold leaves the heads it consumed at -1
   ESVO_CUDA_TRY(c, cudaMemset(ms->d_scal, 0, 4 * 8));
   for (int i = 0; i < 16; ++i) ms->T_world_frame[i] = ms->T_frame_world[i] = (i % 5 == 0) ? 1.0 : 0.0;
-  ESVO_CUDA_TRY(c, cudaMemcpy(ms->d_T_frame_world, ms->T_frame_world, 128, cudaMemcpyHostToDevice));
-  ESVO_CUDA_TRY(c, cudaMemcpy(ms->d_T_frame_world + 16, ms->T_world_frame, 128, cudaMemcpyHostToDevice));
+  ms->list_valid = true; ms->folds = 0;
   return prop_reserve(c, 65536);
 }
 void fuse_free(Ctx* c) {
@@ -546,19 +653,20 @@ void fuse_free(Ctx* c) {
   MapSoA& M = ms->m; PropSoA& P = ms->p;
   void* ps[] = {M.exists, M.rho, M.s2, M.nu, M.var, M.res, M.x0, M.x1, M.pc0, M.pc1, M.pc2, M.rho_tmp, M.age, M.row, M.col,
                 M.first_key, P.hot, P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col,
-                ms->head, ms->next, ms->d_T_frame_world, ms->d_dl, ms->d_dl_keys, ms->d_scal};
+                ms->head, ms->next, ms->active, ms->cbits, ms->cprefix, ms->d_dl, ms->d_dl_keys, ms->d_scal};
   for (void* p : ps) if (p) cudaFree(p);
   if (ms->h_scal) cudaFreeHost(ms->h_scal);
-  if (ms->h_T_ring) cudaFreeHost(ms->h_T_ring);
   delete ms;
   c->map = nullptr;
 }
 
+// New empty DepthFrame at pose T (esvo_Mapping.cpp:268-272).  Two enqueued operations: clear the existence plane and the
+// map scalars {n_fusions, download count, map size, active pixels}.  The frame pose travels to the kernels by value.
 int fuse_reset_map(Ctx* c, const double T[16]) {
   MapState* ms = c->map;
   const size_t npix = (size_t)c->dc.W * c->dc.H;
   ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->m.exists, 0, npix, c->stream));
-  ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->head, 0xff, npix * 4, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->d_scal, 0, 32, c->stream));
   std::memcpy(ms->T_world_frame, T, 128);
   // rigid inverse (kindr Transformation::inverse)
   double* I = ms->T_frame_world;
@@ -566,11 +674,19 @@ int fuse_reset_map(Ctx* c, const double T[16]) {
   I[15] = 1;
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) I[i * 4 + j] = T[j * 4 + i];
   for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += I[i * 4 + k] * T[k * 4 + 3]; I[i * 4 + 3] = -s; }
-  // pinned ring (8 frames deep, far more than the pipeline depth) so that the upload never blocks the host
-  double* hp = ms->h_T_ring + 32 * (ms->ring_idx++ & 7);
-  std::memcpy(hp, ms->T_frame_world, 128); std::memcpy(hp + 16, ms->T_world_frame, 128);
-  ESVO_CUDA_TRY(c, cudaMemcpyAsync(ms->d_T_frame_world, hp, 256, cudaMemcpyHostToDevice, c->stream));
   ms->seq_base = 0; ms->staged = 0;
+  ms->list_valid = true; ms->folds = 0;
+  return ESVO_OK;
+}
+
+// First staging call of a round that does not follow a reset: restart the active list (it then covers this round's pixels
+// only, which is all the fold needs; kernels that need EVERY existing pixel fall back to their full-image form).
+static int fuse_begin_round(Ctx* c) {
+  MapState* ms = c->map;
+  if (ms->staged == 0 && ms->folds > 0) {
+    ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->d_scal + 3, 0, 8, c->stream));
+    ms->list_valid = false;
+  }
   return ESVO_OK;
 }
 
@@ -584,13 +700,16 @@ int fuse_points(Ctx* c, const esvo_depth_point* d_pts, size_t n_cap, const uint6
     int rc = prop_reserve(c, n_cap);
     if (rc) return rc;
   }
-  const int B = 64;    // 64 registers x 64 threads = one LM block's worth (see fuse_finish)
+  int rc = fuse_begin_round(c);
+  if (rc) return rc;
+  const int B = 64;
   FrameSet fs;
   fs.nframes = 1; fs.pts[0] = d_pts; fs.cnt[0] = (const unsigned long long*)d_n; fs.cap[0] = (int)n_cap; fs.off[0] = 0; fs.off[1] = (int)n_cap;
   DevConsts dcs = c->dc;
   if (naive) dcs.lsnorm = ESVO_LSNORM_L2;
-  fuse_stage_kernel<<<div_up((int)n_cap, B), B, 0, c->stream>>>(dcs, fs, ms->d_T_frame_world, radius, (int)ms->staged, ms->p,
-                                                                ms->head, ms->next);
+  Pose16 Tfw; std::memcpy(Tfw.m, ms->T_frame_world, 128);
+  fuse_stage_kernel<<<div_up((int)n_cap, B), B, 0, c->stream>>>(dcs, fs, Tfw, radius, (int)ms->staged, ms->p, ms->head, ms->next,
+                                                                ms->active, ms->d_scal);
   c->launches += 1;
   ms->staged += n_cap;
   ESVO_CUDA_TRY(c, cudaGetLastError());
@@ -601,6 +720,9 @@ int fuse_points(Ctx* c, const esvo_depth_point* d_pts, size_t n_cap, const uint6
 int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
   MapState* ms = c->map;
   const int B = 64;
+  int rc = fuse_begin_round(c);
+  if (rc) return rc;
+  Pose16 Tfw; std::memcpy(Tfw.m, ms->T_frame_world, 128);
   for (int f0 = 0; f0 < nframes; f0 += FS_MAX) {
     FrameSet fs;
     fs.nframes = std::min(FS_MAX, nframes - f0);
@@ -612,7 +734,8 @@ int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
     const int tot = fs.off[fs.nframes];
     if (tot == 0) continue;
     if (ms->staged + (size_t)tot > ms->prop_cap) { c->set_error("fusion staging capacity exceeded"); return ESVO_ERR_CAPACITY; }
-    fuse_stage_kernel<<<div_up(tot, B), B, 0, c->stream>>>(c->dc, fs, ms->d_T_frame_world, radius, (int)ms->staged, ms->p, ms->head, ms->next);
+    fuse_stage_kernel<<<div_up(tot, B), B, 0, c->stream>>>(c->dc, fs, Tfw, radius, (int)ms->staged, ms->p, ms->head, ms->next, ms->active,
+                                                           ms->d_scal);
     c->launches += 1;
     ms->staged += (size_t)tot;
   }
@@ -620,21 +743,33 @@ int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
   return ESVO_OK;
 }
 
-int fuse_finish(Ctx* c, bool naive) {
+// Ordered per-pixel replay of everything staged since the last fold.  clean_* != null: SmartGrid::clean applied to the
+// folded pixels on the way out (whole-frame path: the map was reset, so the folded pixels are all there is).
+int fuse_finish(Ctx* c, bool naive, const double* clean4) {
   MapState* ms = c->map;
   if (ms->staged == 0) return ESVO_OK;
-  // 32-thread blocks (3.4 K registers): a fold block fits into the hole ONE retiring LM block (4 K registers) leaves on
-  // an SM.  With 128-thread blocks (13 K registers) the fold starved behind the LM blocks of the other pipeline slots,
-  // which refill every hole at once: 2-3 ms per frame instead of 0.3 ms (timeline of the 16-slot pipeline).
+  CleanArgs ca{0, 0, 0, 0, 0};
+  if (clean4) { ca.enable = 1; ca.var_thr = clean4[0]; ca.age_thr = clean4[1]; ca.rmax = clean4[2]; ca.rmin = clean4[3]; }
+  // creator bits feed the sort-free ordered hand-off; only meaningful for the first fold after a reset
+  uint32_t* cbits = nullptr;
+  if (ms->list_valid && ms->folds == 0) {
+    ms->fold_words = (ms->staged * 9 + 31) / 32;
+    ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->cbits, 0, ms->fold_words * 4, c->stream));
+    cbits = ms->cbits;
+  }
+  // at most one thread per image pixel can be active; the grid covers that bound, surplus blocks exit on the device count
   const int npix = c->dc.W * c->dc.H, B = 32;
-  if (naive) fuse_fold_kernel<true><<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->seq_base, ms->d_scal);
-  else fuse_fold_kernel<false><<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->seq_base, ms->d_scal);
+  const int bound = (int)std::min<size_t>((size_t)npix, ms->staged * 9);
+  if (naive) fuse_fold_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+  else fuse_fold_kernel<false><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
   c->launches += 1;
   ms->seq_base += (unsigned long long)ms->staged * 9ULL;
   ms->staged = 0;
+  ms->folds++;
   ESVO_CUDA_TRY(c, cudaGetLastError());
   return ESVO_OK;
 }
+static bool list_ok(const MapState* ms) { return ms->list_valid && ms->folds == 1; }
 
 int map_clean(Ctx* c, double var_thr, double age_thr, double rmax, double rmin) {
   const int npix = c->dc.W * c->dc.H, B = 256;
@@ -643,24 +778,46 @@ int map_clean(Ctx* c, double var_thr, double age_thr, double rmax, double rmin) 
   return ESVO_OK;
 }
 
-int map_regularize(Ctx* c) {
-  const int npix = c->dc.W * c->dc.H, B = 32;   // 69 registers: small blocks for the same reason as the fold
-  map_regularize_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, c->map->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
-                                                              c->prm.reg_min_close_neighbours);
-  map_regularize_commit_kernel<<<div_up(npix, 256), 256, 0, c->stream>>>(npix, c->map->m);
+// DepthRegularization::apply; count != 0 also leaves the number of map elements in d_scal[2] (zeroed by the reset).
+int map_regularize(Ctx* c, bool count) {
+  MapState* ms = c->map;
+  const int npix = c->dc.W * c->dc.H, B = 32;
+  if (list_ok(ms)) {
+    const int bound = npix;
+    map_regularize_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
+                                                                      c->prm.reg_min_close_neighbours, ms->active, ms->d_scal);
+    if (count) map_commit_count_list_kernel<<<div_up(bound, 256), 256, 0, c->stream>>>(ms->m, 1, ms->active, ms->d_scal);
+    else map_regularize_commit_kernel<<<div_up(npix, 256), 256, 0, c->stream>>>(npix, ms->m);
+    c->launches += 2;
+    return ESVO_OK;
+  }
+  map_regularize_kernel<false><<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
+                                                                     c->prm.reg_min_close_neighbours, ms->active, ms->d_scal);
+  map_regularize_commit_kernel<<<div_up(npix, 256), 256, 0, c->stream>>>(npix, ms->m);
   c->launches += 2;
+  if (count) return map_count(c);
   return ESVO_OK;
 }
 
 // Enqueue (on c->stream) the compaction of the current map into caller-provided device buffers and the
 // D2H of its scalars: h_scal8[1] = element count, h_scal8[4] = n_fusions, h_scal8[6] = map size.
 // With h_sorted (pinned host memory, npix elements) the elements are also written there in creation order.
+// h_counters (pinned, optional): receives a copy of the frame's kCounters device counters.
 int map_gather_async(Ctx* c, esvo_depth_point* d_out, unsigned long long* d_keys, unsigned long long* d_scal4,
-                     unsigned long long* h_scal8, esvo_depth_point* h_sorted) {
+                     unsigned long long* h_scal8, esvo_depth_point* h_sorted, uint64_t* h_counters) {
   MapState* ms = c->map;
   const int npix = c->dc.W * c->dc.H, B = 128;
+  Pose16 Twf; std::memcpy(Twf.m, ms->T_world_frame, 128);
+  if (h_sorted && list_ok(ms) && ms->fold_words) {
+    // sort-free: rank from the creator bitmap; the kernels write elements, scalars and counters straight into pinned memory
+    map_cbits_prefix_kernel<<<1, 1024, 0, c->stream>>>(ms->cbits, ms->cprefix, (int)ms->fold_words, ms->d_scal, h_scal8, c->d_counters, h_counters);
+    map_gather_list_kernel<<<div_up(npix, B), B, 0, c->stream>>>(ms->m, Twf, ms->active, ms->d_scal, ms->cbits, ms->cprefix, h_sorted);
+    c->launches += 2;
+    ESVO_CUDA_TRY(c, cudaGetLastError());
+    return ESVO_OK;
+  }
   ESVO_CUDA_TRY(c, cudaMemsetAsync(d_scal4, 0, 32, c->stream));
-  map_gather_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->d_T_frame_world + 16, d_out, d_keys, d_scal4);
+  map_gather_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, Twf, d_out, d_keys, d_scal4);
   c->launches += 1;
   if (h_sorted) {
     map_rank_permute_kernel<<<div_up(npix, 256), 256, 0, c->stream>>>(d_out, d_keys, d_scal4, h_sorted);
@@ -668,6 +825,7 @@ int map_gather_async(Ctx* c, esvo_depth_point* d_out, unsigned long long* d_keys
   }
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(h_scal8, d_scal4, 32, cudaMemcpyDeviceToHost, c->stream));
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(h_scal8 + 4, ms->d_scal, 32, cudaMemcpyDeviceToHost, c->stream));
+  if (h_counters) ESVO_CUDA_TRY(c, cudaMemcpyAsync(h_counters, c->d_counters, kCounters * 8, cudaMemcpyDeviceToHost, c->stream));
   ESVO_CUDA_TRY(c, cudaGetLastError());
   return ESVO_OK;
 }
@@ -675,8 +833,9 @@ int map_gather_async(Ctx* c, esvo_depth_point* d_out, unsigned long long* d_keys
 int map_download(Ctx* c, esvo_depth_point* out, size_t* n) {
   MapState* ms = c->map;
   const int npix = c->dc.W * c->dc.H, B = 128;
+  Pose16 Twf; std::memcpy(Twf.m, ms->T_world_frame, 128);
   ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->d_scal + 1, 0, 8, c->stream));
-  map_gather_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, ms->d_T_frame_world + 16, ms->d_dl, ms->d_dl_keys, ms->d_scal);
+  map_gather_kernel<<<div_up(npix, B), B, 0, c->stream>>>(c->dc, ms->m, Twf, ms->d_dl, ms->d_dl_keys, ms->d_scal);
   c->launches += 1;
   ESVO_CUDA_TRY(c, cudaMemcpyAsync(ms->h_scal, ms->d_scal, 32, cudaMemcpyDeviceToHost, c->stream));
   ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -697,9 +856,6 @@ int map_download(Ctx* c, esvo_depth_point* out, size_t* n) {
   return ESVO_OK;
 }
 
-}  // namespace esvo
-
-namespace esvo {
 __global__ void map_count_kernel(int npix, MapSoA M, unsigned long long* scal) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const int e = (pix < npix && M.exists[pix]) ? 1 : 0;
@@ -709,6 +865,11 @@ __global__ void map_count_kernel(int npix, MapSoA M, unsigned long long* scal) {
 // counts existing map pixels into scal[2]
 int map_count(Ctx* c) {
   MapState* ms = c->map;
+  if (list_ok(ms)) {   // scal[2] is still zero from the reset
+    map_commit_count_list_kernel<<<div_up(c->dc.W * c->dc.H, 256), 256, 0, c->stream>>>(ms->m, 0, ms->active, ms->d_scal);
+    c->launches += 1;
+    return ESVO_OK;
+  }
   const int npix = c->dc.W * c->dc.H, B = 256;
   ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->d_scal + 2, 0, 8, c->stream));
   map_count_kernel<<<div_up(npix, B), B, 0, c->stream>>>(npix, ms->m, ms->d_scal);
@@ -729,4 +890,7 @@ int fuse_fetch_scalars(Ctx* c, unsigned long long out[4]) {
 }
 int fuse_reserve(Ctx* c, size_t total_points) { return prop_reserve(c, total_points); }
 const double* fuse_frame_pose(Ctx* c) { return c->map->T_world_frame; }
+// a kernel outside fuse.cu (or an API call that edits the map image-wide) invalidates the "all existing pixels are listed" property
+void fuse_list_invalidate(Ctx* c) { c->map->list_valid = false; }
+
 }  // namespace esvo

@@ -198,10 +198,10 @@ __global__ void ts_decay_median_kernel(const int32_t* __restrict__ scalars, cons
                                        const long long* __restrict__ tmp_idx, const long long* __restrict__ tmp_t,
                                        const uint8_t* __restrict__ tmp_pol, const int32_t* __restrict__ cnt,
                                        int queue_len, long long T, double decay_sec, int ignore_polarity, int W, int H,
-                                       int pitch, long long* __restrict__ out_idx, uint8_t* __restrict__ img) {
+                                       int pitch, long long* __restrict__ out_idx, uint8_t* __restrict__ img, int maybe_general) {
   constexpr int R = KS / 2;
   __shared__ uint8_t tile[TSY + 2 * R][TSX + 2 * R + 2];
-  const bool general = scalars[2] != 0;
+  const bool general = maybe_general && scalars[2] != 0;   // maybe_general == 0: the host knows T is newer than every stamp
   const long long* gi = general ? tmp_idx : cur_idx;
   const long long* gt = general ? tmp_t : cur_t;
   const uint8_t* gp = general ? tmp_pol : cur_pol;
@@ -273,10 +273,10 @@ __global__ void ts_forward_scatter_kernel(const int32_t* __restrict__ scalars, c
                                           const uint8_t* __restrict__ tmp_pol, const int32_t* __restrict__ cnt, int queue_len,
                                           long long T, double decay_sec, int ignore_polarity, int W, int H,
                                           const double* __restrict__ lut, long long* __restrict__ out_idx,
-                                          int32_t* head, int32_t* __restrict__ next, double* __restrict__ val) {
+                                          int32_t* head, int32_t* __restrict__ next, double* __restrict__ val, int maybe_general) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= W * H) return;
-  const bool general = scalars[2] != 0;
+  const bool general = maybe_general && scalars[2] != 0;
   long long idx = general ? tmp_idx[p] : cur_idx[p];
   if (general && idx >= 0 && cnt[p] >= queue_len) idx = -1;   // fell out of the 20-deep queue
   const long long ts = idx >= 0 ? (general ? tmp_t[p] : cur_t[p]) : 0;
@@ -379,6 +379,7 @@ int ts_reset_state(Ctx* c, int cam) {
   if (s.back) ESVO_CUDA_TRY(c, cudaMemsetAsync(s.back, 0, 80, c->stream));
   ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   s.log_n = 0; s.log_base = 0; s.built = false; s.last_img = s.img_out;
+  s.host_knows = true; s.host_max_t = INT64_MIN;
   return ESVO_OK;
 }
 
@@ -449,6 +450,8 @@ int ts_push(Ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t
   const int B = 256;
   unsigned g = (unsigned)((n + B - 1) / B);
   long long gbase = s.log_base + (long long)off;
+  if (dev_src || s.unordered) s.host_knows = false;
+  else if (s.host_knows) { if (t[n - 1] >= s.host_max_t) s.host_max_t = t[n - 1]; else s.host_knows = false; }
   if (s.unordered) {
     const int nb = (int)((n + 1023) / 1024);
     if (!s.back) { ESVO_CUDA_TRY(c, dmalloc(&s.back, 10)); ESVO_CUDA_TRY(c, cudaMemsetAsync(s.back, 0, 80, c->stream)); }
@@ -506,11 +509,16 @@ int ts_run_build(Ctx* c, int cam, int64_t T) {
   const int B = 256;
   cudaEvent_t pe = c->prof_begin(0);
   const unsigned GG = 148 * 4;   // fixed grid, grid-stride loops: these three kernels are no-ops on the fast path
-  ts_general_init_kernel<<<GG, B, 0, c->stream>>>(
-      s.scalars, s.et, s.log_n, T, npix, (const long long*)s.base_idx, (const long long*)s.base_t, s.base_pol, (long long*)s.tmp_idx,
-      (long long*)s.tmp_t, s.tmp_pol, s.cnt);
-  c->launches += 1;
-  if (s.log_n) {
+  // T newer than every pushed stamp (known on the host for host-buffer pushes of ordered input): the most-recent-event grid
+  // IS the answer and the general path's three launches (no-ops on the device in that case) are not issued at all
+  const int maybe_general = (s.host_knows && (s.log_n == 0 || T > s.host_max_t)) ? 0 : 1;
+  if (maybe_general) {
+    ts_general_init_kernel<<<GG, B, 0, c->stream>>>(
+        s.scalars, s.et, s.log_n, T, npix, (const long long*)s.base_idx, (const long long*)s.base_t, s.base_pol, (long long*)s.tmp_idx,
+        (long long*)s.tmp_t, s.tmp_pol, s.cnt);
+    c->launches += 1;
+  }
+  if (maybe_general && s.log_n) {
     ts_general_scatter_kernel<<<GG, B, 0, c->stream>>>(s.scalars, s.ex, s.ey, s.log_n, s.log_base, d.W, d.H,
                                                       (long long*)s.tmp_idx, s.cnt);
     ts_general_fix_kernel<<<GG, B, 0, c->stream>>>(s.scalars, s.ex, s.ey, s.et, s.ep, s.log_n, s.log_base, d.W, d.H,
@@ -527,12 +535,12 @@ int ts_run_build(Ctx* c, int cam, int64_t T) {
       ts_decay_median_kernel<3><<<grd, blk, 0, c->stream>>>(
           s.scalars, (const long long*)s.cur_idx, (const long long*)s.cur_t, s.cur_pol, (const long long*)s.tmp_idx,
           (const long long*)s.tmp_t, s.tmp_pol, s.cnt, c->prm.max_event_queue_len, T, decay_sec, c->prm.ignore_polarity,
-          d.W, d.H, d.pitch, (long long*)s.out_idx, s.img_med);
+          d.W, d.H, d.pitch, (long long*)s.out_idx, s.img_med, maybe_general);
     else
       ts_decay_median_kernel<1><<<grd, blk, 0, c->stream>>>(
           s.scalars, (const long long*)s.cur_idx, (const long long*)s.cur_t, s.cur_pol, (const long long*)s.tmp_idx,
           (const long long*)s.tmp_t, s.tmp_pol, s.cnt, c->prm.max_event_queue_len, T, decay_sec, c->prm.ignore_polarity,
-          d.W, d.H, d.pitch, (long long*)s.out_idx, s.img_med);
+          d.W, d.H, d.pitch, (long long*)s.out_idx, s.img_med, maybe_general);
     dim3 b2(32, 8), g2(div_up(d.W, 32), div_up(d.H, 8));
     ts_remap_kernel<<<g2, b2, 0, c->stream>>>(s.img_med, s.map1, s.map2, d.W, d.H, d.pitch, s.img_out);
     c->launches += 2;
@@ -552,7 +560,7 @@ int ts_run_build(Ctx* c, int cam, int64_t T) {
     ts_forward_scatter_kernel<<<div_up((int)npix, B), B, 0, c->stream>>>(
         s.scalars, (const long long*)s.cur_idx, (const long long*)s.cur_t, s.cur_pol, (const long long*)s.tmp_idx,
         (const long long*)s.tmp_t, s.tmp_pol, s.cnt, c->prm.max_event_queue_len, T, decay_sec, c->prm.ignore_polarity, d.W, d.H,
-        s.fwd_lut, (long long*)s.out_idx, s.fwd_head, s.fwd_next, s.fwd_val);
+        s.fwd_lut, (long long*)s.out_idx, s.fwd_head, s.fwd_next, s.fwd_val, maybe_general);
     ts_forward_fold_kernel<<<div_up((int)npix, B), B, 0, c->stream>>>(d.W, d.H, d.pitch, s.fwd_head, s.fwd_next, s.fwd_val,
                                                                      c->prm.ignore_polarity, ks == 3 ? s.img_med : s.img_out);
     c->launches += 2;

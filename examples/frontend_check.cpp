@@ -14,6 +14,18 @@ int main() {
   for (size_t i = 1; i < sel.size(); ++i) if (sel[i]->ts >= sel[i - 1]->ts) bad |= 4;   // newest first
   selectCloseEvents(ev, t_end, 0.00001, 1000, sel);                             // window of 100 us -> 100 events
   if (sel.size() != 100) bad |= 8;
+  // observation stamp newer than every buffered event: the newest events are still selected (one budget slot goes to
+  // the reference's one-past-the-end read)
+  {
+    std::vector<esvo::Event*> s2;
+    const int64_t t_new = ev.back().ts + 5000;
+    selectCloseEvents(ev, t_new, 0.001, 1000, s2);
+    if (s2.size() != 999 || s2.front() != &ev.back()) bad |= 4096;
+    selectCloseEvents(ev, t_new, 0.0000001, 1000, s2);            // 1 us window: lower_bound(t_begin) == end as well -> nothing
+    if (!s2.empty()) bad |= 8192;
+    selectSGMEvents(ev, t_new, 0.001, 1000, s2);                  // 2 ms window = 2000 events available, budget 1001 - 1
+    if (s2.size() != 1000 || s2.front() != &ev.back()) bad |= 16384;
+  }
   auto st = samplePoseStamps(t_end, 0.001);
   if (st.size() != 201) bad |= 16;                                             // 10 ms window / 50 us
   if (!st.empty() && (st.front() != t_end - 10000000 || st.back() > t_end)) bad |= 32;

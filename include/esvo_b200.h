@@ -316,8 +316,14 @@ ESVO_API int esvo_set_pipeline_depth(esvo_ctx* ctx, int depth);
 ESVO_API int esvo_results_begin(esvo_ctx* ctx, int64_t* ticket_out);
 ESVO_API int esvo_results_end(esvo_ctx* ctx, int64_t ticket, esvo_depth_point* out, size_t* n,
                               uint64_t* counters_out);
+/* Zero-copy form of esvo_results_end: *out points into the slot's pinned host landing buffer, which the gather kernel
+ * filled over PCIe (element-list order); it stays valid until that slot's next esvo_results_begin. */
+ESVO_API int esvo_results_end_view(esvo_ctx* ctx, int64_t ticket, const esvo_depth_point** out, size_t* n,
+                                   uint64_t* counters_out);
 /* Device-pointer forms (suffix _dev): the arrays are CUDA device pointers on the ctx's device, i.e.
  * the inputs are already resident in HBM; work is enqueued on the ctx stream, nothing is synchronised.
+ * esvo_stage_mapping_inputs_dev uses its arrays IN PLACE (no copy): keep them valid and unchanged until the frame has
+ * been collected with esvo_results_end or the ctx synchronised.
  * esvo_set_ts_pair_dev hands the images of the last two esvo_run_ts_build calls to the mapper. */
 ESVO_API int esvo_ts_push_events_dev(esvo_ctx* ctx, int cam, const uint16_t* x_dev, const uint16_t* y_dev,
                                      const int64_t* t_ns_dev, const uint8_t* pol_dev, size_t n);

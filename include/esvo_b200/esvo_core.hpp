@@ -267,9 +267,14 @@ inline void selectCloseEvents(std::vector<esvo::Event>& events_left /* time-orde
   };
   size_t ev_end = lower(t_end_ns);
   const size_t ev_begin = lower(t_begin_ns);
-  if (ev_end == events_left.size()) return;   // the reference dereferences end() here (UB); no event at/after t_end -> nothing to add
-  while (ev_end != ev_begin && vCloseEventsPtr_left.size() < PROCESS_EVENT_NUM) {
-    vCloseEventsPtr_left.push_back(&events_left[ev_end]);   // note: starts AT lower_bound(t_end), like the reference (:570-574)
+  // The walk starts AT lower_bound(t_end) and stops before lower_bound(t_begin) (:570-574).  When no event is at/after
+  // t_end (the observation stamp is newer than the whole buffer -- the common case online) the reference's first push is
+  // deque::end()._M_cur, one slot past the newest event (UB: an unconstructed event); it then still walks back over the
+  // newest valid events.  We skip only that slot but keep its place in the PROCESS_EVENT_NUM budget.
+  size_t budget = PROCESS_EVENT_NUM;
+  if (ev_end == events_left.size() && ev_end != ev_begin && budget > 0) { --ev_end; --budget; }
+  while (ev_end != ev_begin && vCloseEventsPtr_left.size() < budget) {
+    vCloseEventsPtr_left.push_back(&events_left[ev_end]);
     --ev_end;
   }
 }
@@ -287,8 +292,9 @@ inline void selectSGMEvents(std::vector<esvo::Event>& events_left, int64_t t_end
   };
   size_t ev_end = lower(t_end_ns);
   const size_t ev_begin = lower(t_begin_ns);
-  if (ev_end == events_left.size()) return;   // the reference dereferences end() here (UB)
-  while (ev_end != ev_begin && vEventsPtr_left_SGM.size() <= PROCESS_EVENT_NUM) { vEventsPtr_left_SGM.push_back(&events_left[ev_end]); --ev_end; }
+  size_t budget = PROCESS_EVENT_NUM + 1;      // `<=` on the count: one event more than PROCESS_EVENT_NUM
+  if (ev_end == events_left.size() && ev_end != ev_begin) { --ev_end; --budget; }   // skip the one-past-the-end slot (see selectCloseEvents)
+  while (ev_end != ev_begin && vEventsPtr_left_SGM.size() < budget) { vEventsPtr_left_SGM.push_back(&events_left[ev_end]); --ev_end; }
 }
 inline std::vector<int64_t> samplePoseStamps(int64_t t_end_ns, double BM_half_slice_thickness) {
   std::vector<int64_t> out;

@@ -338,6 +338,10 @@ struct EventBM {
 static thread_local uint64_t g_irls_iters = 0, g_irls_max = 0;  // diagnostics of the calling thread
 static thread_local uint64_t g_irls_hist[8] = {0};  // non-degenerate evals by iteration count: <=4,<=8,<=16,<=32,<=64,<=256,<=1024,more
 static thread_local uint64_t g_irls_nd_iters = 0, g_irls_deg = 0;
+// TIMING AID ONLY (bench.py cpu_baseline.with_shortcut), default off so that parity stays literal: skip the reference's
+// degenerate scale iteration the way the CUDA kernel does (lm.cu "degenerate regime": with m non-zero residuals and
+// (nu+1) m / N < 0.95 the loop of DepthProblem.cpp:96 can only end through sum == 0 -> scale = td_scale^2).
+static int g_irls_shortcut = 0;
 struct DepthProblem {
   const CameraSystem* cs = nullptr;
   const TsObs* obs = nullptr;
@@ -409,6 +413,11 @@ struct DepthProblem {
         double s1 = td_scale2, s2 = -1.0;
         bool first = true;
         uint64_t loc = 0;
+        if (g_irls_shortcut) {
+          int nzs = 0; double rmin = 1e300;
+          for (int i = 0; i < N; ++i) { vR[i] = tau1[i] - tau2[i]; vR2[i] = vR[i] * vR[i]; if (vR[i] != 0) { nzs++; rmin = std::min(rmin, std::fabs(vR[i])); } }
+          if ((td_nu + 1) * (double)nzs < 0.95 * (double)N * (1.0 - 1e-9) && rmin > 1e-6) { s2 = td_scale2; first = false; s1 = s2; }
+        }
         while (std::fabs(s2 - s1) / s1 > 0.05 || first) {           // :96
           ++g_irls_iters; if (++loc > g_irls_max) g_irls_max = loc;
           if (!first) s1 = s2;

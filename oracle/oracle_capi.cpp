@@ -211,6 +211,7 @@ OAPI int esvo_oracle_window_download(esvo_oracle_ctx* c, int index, esvo_depth_p
   *n = v.size();
   return ESVO_OK;
 }
+OAPI int esvo_oracle_set_irls_shortcut(int on) { g_irls_shortcut = on ? 1 : 0; return ESVO_OK; }   // timing aid, see o_mapping.h
 OAPI int esvo_oracle_set_exec_threads(esvo_oracle_ctx* c, int n) { c->exec_threads = n < 1 ? 1 : n; return ESVO_OK; }
 OAPI int esvo_oracle_mapping_reset(esvo_oracle_ctx* c) { c->window.clear(); return ESVO_OK; }
 
