@@ -34,6 +34,12 @@ __global__ void gauss5_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __res
   dst[(size_t)y * pitch + x] = (uint8_t)((s + 128) >> 8);
 }
 
+__global__ void fp64_probe_kernel(double* out, int iters) {
+  double a = threadIdx.x * 1e-3 + 1.0, b = 1.000001, cc = 0.5, d = a + 1;
+  for (int i = 0; i < iters; ++i) { a = fma(a, b, cc); d = fma(d, b, cc); }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a + d;
+}
+
 int smooth_obs(Ctx* c) {
   dim3 b(32, 8), g(div_up(c->dc.W, 32), div_up(c->dc.H, 8));
   c->obs_ls = c->slots[c->cur].own_ls; c->obs_rs = c->slots[c->cur].own_rs;
@@ -216,6 +222,35 @@ ESVO_API int esvo_debug_lm_timing(esvo_ctx* c, long long* out, size_t n) {
   return ESVO_OK;
 }
 ESVO_API int esvo_sync(esvo_ctx* c) { CHECK_CTX(c); return drain(c); }
+// Measured FP64 FMA rate of this GPU (bench.py: the denominator of the fp64 roofline): 148*8 blocks x 256 threads, two
+// independent dependent-FMA chains per thread, CUDA-event timed on the ctx stream.  Returns TFLOP/s (2 flops per FMA).
+ESVO_API int esvo_debug_fp64_probe(esvo_ctx* c, double* tflops_out) {
+  CHECK_CTX(c);
+  if (!tflops_out) return ESVO_ERR_INVALID_ARG;
+  int rc = drain(c);
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  ESVO_CUDA_TRY(c, cudaGetDeviceProperties(&prop, c->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double* out = nullptr;
+  ESVO_CUDA_TRY(c, dmalloc(&out, (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  fp64_probe_kernel<<<blocks, threads, 0, c->stream>>>(out, 64);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0, c->stream);
+    fp64_probe_kernel<<<blocks, threads, 0, c->stream>>>(out, iters);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  ESVO_CUDA_TRY(c, cudaGetLastError());
+  *tflops_out = 2.0 * 2.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+  return ESVO_OK;
+}
 ESVO_API int esvo_set_pipeline_depth(esvo_ctx* c, int depth) {
   CHECK_CTX(c);
   if (depth < 1 || depth > kMaxSlots) return ESVO_ERR_INVALID_ARG;
@@ -507,7 +542,9 @@ ESVO_API int esvo_set_ts_pair_dev(esvo_ctx* c, const double T[16]) {
 static int run_bm_stage(esvo_ctx* c) {
   if (c->prm.smooth_time_surface) { int rc = smooth_obs(c); if (rc) return rc; }  // EventBM.cpp:68-72
   ESVO_CUDA_TRY(c, cudaMemsetAsync(c->d_counters, 0, kCounters * 8, c->stream));
+  cudaEvent_t pe = c->prof_begin(1);
   int rc = bm_run(c);
+  c->prof_end(pe);
   if (rc) return rc;
   return seeds_order(c);
 }

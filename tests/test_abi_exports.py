@@ -25,7 +25,7 @@ def test_header_symbols_exported(product_lib, oracle_lib):
         if n.endswith("_dev") or n in ("esvo_stage_ts_events", "esvo_run_ts_build", "esvo_stage_mapping_inputs",
                                        "esvo_run_mapping", "esvo_fetch_mapping_counters", "esvo_sync", "esvo_stream",
                                        "esvo_launch_count", "esvo_last_error", "esvo_debug_counter", "esvo_profile",
-                                       "esvo_profile_read", "esvo_set_pipeline_depth", "esvo_results_begin", "esvo_results_end",
+                                       "esvo_profile_read", "esvo_set_pipeline_depth", "esvo_results_begin", "esvo_results_end", "esvo_results_end_view",
                                        "esvo_compute_rectify_tables",   # host set-up of the product, pinned to cv2 directly
                                        "esvo_sgbm_compute"):   # its oracle is oracle/sgbm.py (numpy, pinned against cv2)
             continue
