@@ -421,7 +421,8 @@ def parity_block(prod, base, rig, n_check=3, tracking=True):
     """The benchmarked frames through the product (fresh ctx, depth 1) and through the CPU oracle, both on the PRODUCT's own
     rectification tables: fusion window primed to its full length, then n_check consecutive frames compared stage by stage."""
     from esvo_b200 import capi, configs, dist as edist
-    orc = capi.load_oracle()
+    from oracle.loader import load_oracle
+    orc = load_oracle()
     l, r = configs.rig_calibs(rig)
     pp, po = configs.params_for(rig, prod), configs.params_for(rig, orc)
     g = capi.Backend(prod, l, r, pp)
@@ -495,9 +496,11 @@ def parity_block(prod, base, rig, n_check=3, tracking=True):
     if l1:
         a = np.concatenate(l1)
         res["inv_depth_l1"] = float(a.mean()) if a.size else 0.0; res["inv_depth_max_rel"] = float(a.max()) if a.size else 0.0
+        res["inv_depth_frac_above_1e-4"] = float((a > 1e-4).mean()) if a.size else 0.0
     if l1m:
         a = np.concatenate(l1m)
         res["map_inv_depth_l1"] = float(a.mean()) if a.size else 0.0; res["map_inv_depth_max_rel"] = float(a.max()) if a.size else 0.0
+        res["map_inv_depth_frac_above_1e-4"] = float((a > 1e-4).mean()) if a.size else 0.0
     res["seconds"] = time.perf_counter() - t0
     extra = tracking_block(g, o, pp, last) if (tracking and last is not None) else None
     g.close(); o.close()
@@ -762,7 +765,8 @@ def _shutdown_pg():
 def cpu_leg(base, sample_steps, threads=None, shortcut=False, rig=RIG):
     """The oracle (a port of the reference CPU path) on the host cores: bounded sample of the same workload."""
     from esvo_b200 import capi, configs
-    orc = capi.load_oracle()
+    from oracle.loader import load_oracle
+    orc = load_oracle()
     l, r = configs.rig_calibs(rig)
     o = capi.Backend(orc, l, r, configs.params_for(rig, orc))
     nthreads = threads or (os.cpu_count() or 1)

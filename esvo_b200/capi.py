@@ -1,8 +1,8 @@
 """ctypes binding of the C ABI declared in include/esvo_b200.h.
 
-The same `Backend` class binds either
-  * the product library  esvo_b200/_build/libesvo_b200.so   (prefix "esvo_",  CUDA, sm_100a), or
-  * the CPU oracle       oracle/_build/libesvo_oracle.so    (prefix "esvo_oracle_", TEST ONLY).
+The `Backend` class binds any library that exports the ABI under some prefix:
+  * the product library  esvo_b200/_build/libesvo_b200.so   (prefix "esvo_",  CUDA, sm_100a) -- load_product() below;
+  * the CPU oracle (prefix "esvo_oracle_") is loaded by oracle/loader.py, which lives OUTSIDE this package (test infrastructure).
 
 The product path never falls back to the oracle: `load_product()` raises if the CUDA library
 is missing, and `esvo_create` fails with ESVO_ERR_NO_DEVICE when there is no usable GPU.
@@ -17,7 +17,6 @@ import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PRODUCT_LIB = os.path.join(_ROOT, "esvo_b200", "_build", "libesvo_b200.so")
-ORACLE_LIB = os.path.join(_ROOT, "oracle", "_build", "libesvo_oracle.so")
 
 ESVO_OK = 0
 ERR_NAMES = {0: "OK", -1: "INVALID_ARG", -2: "NO_DEVICE", -3: "CUDA", -4: "CAPACITY", -5: "STATE",
@@ -110,13 +109,6 @@ def load_product() -> Library:
             f"{PRODUCT_LIB} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback for the product path)")
     return Library(C.CDLL(PRODUCT_LIB), "esvo_", PRODUCT_LIB)
-
-
-def load_oracle() -> Library:
-    """TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench cpu_baseline/reference legs)."""
-    if not os.path.exists(ORACLE_LIB):
-        raise RuntimeError(f"{ORACLE_LIB} is missing: run `make -C oracle`")
-    return Library(C.CDLL(ORACLE_LIB), "esvo_oracle_", ORACLE_LIB)
 
 
 def default_params(lib: Library) -> Params:

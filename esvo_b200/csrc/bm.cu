@@ -190,21 +190,32 @@ __device__ __forceinline__ int tm_index(int v, int n, int NT) {
   return c + (v - start) * NT;
 }
 
-__global__ void __launch_bounds__(1024) seeds_order_kernel(DevConsts dc, BmDense d, const uint16_t* __restrict__ ex,
-                                                           const uint16_t* __restrict__ ey, const int64_t* __restrict__ et,
-                                                           const double* __restrict__ poses, int n, esvo_seed* out,
-                                                           unsigned long long* counters) {
+// Multi-block ordered compaction without inter-block communication: block b owns the virtual positions [256 b, 256 b + 256)
+// of the thread-major order; its base offset is the number of accepted events at EARLIER virtual positions, which the block
+// simply counts itself (b x 256 flag reads, L2-resident -- a few thousand flags in total), followed by a block scan of its own
+// 256 flags.  No look-back state, nothing to zero, every block independent.  The last block publishes the total.
+constexpr int kOrdBlock = 256;
+__global__ void __launch_bounds__(kOrdBlock) seeds_order_kernel(DevConsts dc, BmDense d, const uint16_t* __restrict__ ex,
+                                                                const uint16_t* __restrict__ ey, const int64_t* __restrict__ et,
+                                                                const double* __restrict__ poses, int n, esvo_seed* out,
+                                                                unsigned long long* counters) {
   __shared__ int s_warp[33];
+  __shared__ int s_base;
   const int NT = dc.NT;
-  const int ipt = (n + blockDim.x - 1) / blockDim.x;
-  const int v0 = threadIdx.x * ipt, v1 = min(n, v0 + ipt);
-  int cnt = 0;
-  for (int v = v0; v < v1; ++v) cnt += d.flag[tm_index(v, n, NT)];
+  const int v0 = blockIdx.x * kOrdBlock;
+  if (v0 >= n) return;
+  int pre = 0;
+  for (int v = threadIdx.x; v < v0; v += kOrdBlock) pre += d.flag[tm_index(v, n, NT)];
+  int tot_pre;
+  block_excl_scan(pre, s_warp, tot_pre);
+  if (threadIdx.x == 0) s_base = tot_pre;
+  const int v = v0 + threadIdx.x;
+  const int i = v < n ? tm_index(v, n, NT) : 0;
+  const int f = v < n ? d.flag[i] : 0;
   int total;
-  int pos = block_excl_scan(cnt, s_warp, total);
-  for (int v = v0; v < v1; ++v) {
-    const int i = tm_index(v, n, NT);
-    if (!d.flag[i]) continue;
+  const int local = block_excl_scan(f, s_warp, total);
+  const int pos = s_base + local;
+  if (f) {
     esvo_seed s;
     s.x_left_raw[0] = (double)ex[i]; s.x_left_raw[1] = (double)ey[i];
     const double xr0 = d.xrect[2 * i], xr1 = d.xrect[2 * i + 1];
@@ -219,9 +230,9 @@ __global__ void __launch_bounds__(1024) seeds_order_kernel(DevConsts dc, BmDense
     const double disparity = (double)disp;
     const double depth = dc.baseline * dc.Pl[0] / disparity;           // EventBM.cpp:152
     s.inv_depth = 1.0 / depth; s.cost = d.cost[i]; s.disp = disparity;
-    out[pos++] = s;
+    out[pos] = s;
   }
-  if (threadIdx.x == 0) counters[1] = (unsigned long long)total;
+  if (v0 + kOrdBlock >= n && threadIdx.x == 0) counters[1] = (unsigned long long)(s_base + total);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -240,8 +251,9 @@ int bm_run(Ctx* c) {
 }
 
 int seeds_order(Ctx* c) {
-  seeds_order_kernel<<<1, kOrderThreads, 0, c->stream>>>(c->dc, c->bm, c->d_ex, c->d_ey, c->d_et, c->d_poses, (int)c->n_ev,
-                                                c->d_seeds, (unsigned long long*)c->d_counters);
+  if (c->n_ev == 0) return ESVO_OK;          // counters[1] stays 0 from the frame's memset
+  seeds_order_kernel<<<div_up((int)c->n_ev, kOrdBlock), kOrdBlock, 0, c->stream>>>(c->dc, c->bm, c->d_ex, c->d_ey, c->d_et, c->d_poses, (int)c->n_ev,
+                                                                                 c->d_seeds, (unsigned long long*)c->d_counters);
   c->launches += 1;
   ESVO_CUDA_TRY(c, cudaGetLastError());
   return ESVO_OK;

@@ -15,6 +15,7 @@
 // sequence numbers).  The map is a dense SoA over the image (the SmartGrid's element list order
 // is kept as a "first touched" sequence number per pixel).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -370,6 +371,101 @@ __global__ void map_regularize_kernel(DevConsts dc, MapSoA M, int radius, int mi
     }
   }
   M.rho_tmp[pix] = isSet ? mean : -1.0;
+}
+// Warp-cooperative form over the active list (one fold since the reset): one warp per listed pixel, lanes = 32 consecutive
+// neighbours of the (2r+1)^2 window in raster order.  Validity / closeness tests run lane-parallel; the order-dependent
+// Student-t merge of the close neighbours (DepthRegularization.cpp:63-86: sequential, non-associative in floating point) is
+// replayed in raster order by broadcasting one close neighbour at a time.  Same arithmetic, same order as the thread form
+// above; what changes is the latency: 121 (r = 5) ... 1681 (r = 20) dependent neighbour visits become 4 ... 53 chunk loads.
+__global__ void __launch_bounds__(256) map_regularize_warp_kernel(DevConsts dc, MapSoA M, int radius, int min_nb, int min_close,
+                                                                  const int32_t* __restrict__ active, const unsigned long long* __restrict__ scal) {
+  const unsigned FULLM = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nwarps = gridDim.x * wpb;
+  const int n_active = (int)scal[3];
+  const int side = 2 * radius + 1, nn = side * side;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < n_active; t += nwarps) {
+    const int pix = active[t];
+    if (!M.exists[pix]) continue;
+    const double rho = M.rho[pix];
+    if (!(rho > -1e-6)) { if (lane == 0) M.rho_tmp[pix] = rho; continue; }
+    const int row = pix / dc.W, col = pix - row * dc.W;
+    bool isSet = false;
+    double mean = 0;
+    if (row >= radius && col >= radius) {   // SmartGrid::getNeighbourhood's int/size_t loop never runs otherwise (SmartGrid.h:373-375)
+      const double sig = 2.0 * sqrt(M.var[pix]);
+      int nb = 0, nclose = 0;
+      double nu_post = 0, rho_post = 0, s2_post = 0, tot = 0;
+      for (int k0 = 0; k0 < nn; k0 += 32) {
+        const int k = k0 + lane;
+        bool valid = false, close = false;
+        double qr = 0, qv = 0;
+        int q = 0;
+        if (k < nn) {
+          const int dr = k / side, dcc = k - dr * side;
+          const int r = row - radius + dr, c = col - radius + dcc;
+          if (r < dc.H && c < dc.W) {
+            q = r * dc.W + c;
+            if (M.exists[q]) {
+              qr = M.rho[q];
+              if (qr > -1e-6) {
+                valid = true;
+                qv = M.var[q];
+                const double diff = fabs(rho - qr);
+                close = diff < sig || diff < 2.0 * sqrt(qv);
+              }
+            }
+          }
+        }
+        nb += __popc(__ballot_sync(FULLM, valid));
+        unsigned cm = __ballot_sync(FULLM, close);
+        double q_nu = 0, q_s2 = 0;
+        if (close && dc.lsnorm != ESVO_LSNORM_L2) { q_nu = M.nu[q]; q_s2 = M.s2[q]; }
+        while (cm) {
+          const int src = __ffs(cm) - 1;
+          cm &= cm - 1;
+          const double rho_obs = __shfl_sync(FULLM, qr, src);
+          if (dc.lsnorm == ESVO_LSNORM_L2) tot += 1.0 / __shfl_sync(FULLM, qv, src);
+          else {
+            const double nu_obs = __shfl_sync(FULLM, q_nu, src), s2_obs = __shfl_sync(FULLM, q_s2, src);
+            if (nclose == 0) { nu_post = nu_obs; rho_post = rho_obs; s2_post = s2_obs; }
+            else {
+              const double nu_prior = nu_post, rho_prior = rho_post, s2_prior = s2_post;
+              nu_post = fmin(nu_prior, nu_obs);
+              rho_post = (s2_obs * rho_prior + s2_prior * rho_obs) / (s2_obs + s2_prior);
+              const double d = rho_prior - rho_obs;
+              s2_post = (nu_post + (d * d) / (s2_prior + s2_obs)) / (nu_post + 1) * (s2_prior * s2_obs) / (s2_prior + s2_obs);
+            }
+          }
+          nclose++;
+        }
+      }
+      if (nb > min_nb && nclose > min_close) {
+        if (dc.lsnorm == ESVO_LSNORM_L2) {
+          for (int k0 = 0; k0 < nn; k0 += 32) {      // second sweep: mean += qr * (1/var) / tot in raster order
+            const int k = k0 + lane;
+            bool close = false; double qr = 0, qv = 1;
+            if (k < nn) {
+              const int dr = k / side, dcc = k - dr * side;
+              const int r = row - radius + dr, c = col - radius + dcc;
+              if (r < dc.H && c < dc.W) {
+                const int q = r * dc.W + c;
+                if (M.exists[q]) { qr = M.rho[q]; if (qr > -1e-6) { qv = M.var[q]; const double diff = fabs(rho - qr); close = diff < sig || diff < 2.0 * sqrt(qv); } }
+              }
+            }
+            unsigned cm = __ballot_sync(FULLM, close);
+            while (cm) {
+              const int src = __ffs(cm) - 1; cm &= cm - 1;
+              mean += __shfl_sync(FULLM, qr, src) * (1.0 / __shfl_sync(FULLM, qv, src)) / tot;
+            }
+          }
+        } else mean = rho_post;
+        isSet = true;
+      }
+    }
+    if (lane == 0) M.rho_tmp[pix] = isSet ? mean : -1.0;
+  }
 }
 __global__ void map_regularize_commit_kernel(int npix, MapSoA M) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -784,8 +880,13 @@ int map_regularize(Ctx* c, bool count) {
   const int npix = c->dc.W * c->dc.H, B = 32;
   if (list_ok(ms)) {
     const int bound = npix;
-    map_regularize_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
-                                                                      c->prm.reg_min_close_neighbours, ms->active, ms->d_scal);
+    static const int dbg_thread_form = getenv("ESVO_DBG_REG_THREAD") ? 1 : 0;     // experiment switch: the thread-per-pixel list form
+    if (dbg_thread_form)
+      map_regularize_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
+                                                                        c->prm.reg_min_close_neighbours, ms->active, ms->d_scal);
+    else   // persistent: 148 SMs x 8 blocks of 8 warps walk the active list
+      map_regularize_warp_kernel<<<148 * 8, 256, 0, c->stream>>>(c->dc, ms->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
+                                                                c->prm.reg_min_close_neighbours, ms->active, ms->d_scal);
     if (count) map_commit_count_list_kernel<<<div_up(bound, 256), 256, 0, c->stream>>>(ms->m, 1, ms->active, ms->d_scal);
     else map_regularize_commit_kernel<<<div_up(npix, 256), 256, 0, c->stream>>>(npix, ms->m);
     c->launches += 2;

@@ -12,6 +12,9 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <deque>
+#include <functional>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -397,5 +400,117 @@ class esvo_Mapping {
   void reset() { esvo_mapping_reset(cs_->ctx()); }
  private:
   esvo::CameraSystem::Ptr cs_;
+};
+
+// esvo_core::esvo_Tracking (esvo_Tracking.h:51-53; esvo_Tracking.cpp:79-265 TrackingLoop / refDataTransferring /
+// curDataTransferring, :279-377 callbacks) without ROS.  The subscriptions become plain methods that fill the same buffers
+// (refPCMap_, TS_history_, events_left_); the tf look-up becomes a pose provider; one pass of TrackingLoop's body is
+// TrackingLoopOnce().  The registration itself runs on the device through RegProblemSolverLM (esvo_track_reset/solve).
+class esvo_Tracking {
+ public:
+  enum TrackingStatus { IDLE, WORKING };
+  using PoseProvider = std::function<bool(int64_t /*stamp ns*/, esvo::Pose& /*T_world_dvs*/)>;   // getPoseAt (:359-377)
+  esvo_Tracking(esvo::CameraSystem::Ptr cs, core::RegProblemType rpType = core::REG_ANALYTICAL, size_t TS_HISTORY_LENGTH = 100,
+                size_t REF_HISTORY_LENGTH = 5)
+      : rpSolver_(cs, rpType), cs_(cs), rpType_(rpType), TS_HISTORY_LENGTH_(TS_HISTORY_LENGTH), REF_HISTORY_LENGTH_(REF_HISTORY_LENGTH) {
+    T_world_cur_ = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  }
+  void setPoseProvider(PoseProvider f) { getPoseAt_ = std::move(f); }
+  // ---- callbacks (:279-357) ----
+  // refMapCallback: the local map as the mapping node publishes it (pcl::PointXYZ: f32 x,y,z in the WORLD frame, i.e. the
+  // output of frontend::packPointCloud); at most REF_HISTORY_LENGTH maps are kept.
+  void refMapCallback(int64_t stamp_ns, const std::vector<float>& xyz) {
+    refPCMap_[stamp_ns] = std::make_shared<std::vector<float>>(xyz);
+    while (refPCMap_.size() > REF_HISTORY_LENGTH_) refPCMap_.erase(refPCMap_.begin());
+  }
+  // timeSurfaceCallback: mono8 left image (H*W); the tracker only reads the left one (:331-349).
+  void timeSurfaceCallback(int64_t stamp_ns, const uint8_t* time_surface_left) {
+    const size_t n = (size_t)cs_->width_ * cs_->height_;
+    TS_history_[stamp_ns] = TsEntry{std::vector<uint8_t>(time_surface_left, time_surface_left + n), TS_id_++};
+    while (TS_history_.size() > TS_HISTORY_LENGTH_) TS_history_.erase(TS_history_.begin());
+  }
+  // eventsCallback: insertion-sorted event buffer, capped at 5e6 (:294-321)
+  void eventsCallback(const std::vector<esvo::Event>& events) {
+    for (const esvo::Event& e : events) {
+      events_left_.push_back(e);
+      long i = (long)events_left_.size() - 2;
+      while (i >= 0 && events_left_[(size_t)i].ts > e.ts) { events_left_[(size_t)i + 1] = events_left_[(size_t)i]; --i; }
+      events_left_[(size_t)(i + 1)] = e;
+    }
+    static constexpr size_t MAX_EVENT_QUEUE_LENGTH = 5000000;
+    if (events_left_.size() > MAX_EVENT_QUEUE_LENGTH)
+      events_left_.erase(events_left_.begin(), events_left_.begin() + (long)(events_left_.size() - MAX_EVENT_QUEUE_LENGTH));
+  }
+  // ---- refDataTransferring (:177-211) ----
+  bool refDataTransferring() {
+    ref_.t_ = refPCMap_.rbegin()->first;
+    if (ESVO_System_Status_ == "INITIALIZATION" && ets_ == IDLE) ref_.tr_ = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if (ESVO_System_Status_ == "WORKING" || (ESVO_System_Status_ == "INITIALIZATION" && ets_ == WORKING)) {
+      if (!getPoseAt_ || !getPoseAt_(ref_.t_, ref_.tr_)) return false;   // the reference exit(-1)s here ("logic error")
+    }
+    ref_.vPointXYZ_ = *refPCMap_.rbegin()->second;    // the reference keeps pointers into the cloud; the device path permutes a copy
+    return true;
+  }
+  // ---- curDataTransferring (:213-245) ----
+  bool curDataTransferring() {
+    const size_t ev_last = lower_bound_ev(cur_.t_);
+    auto TS_it = TS_history_.rbegin();
+    if (cur_.t_ == TS_it->first) return false;        // TS_history may not have been updated yet
+    cur_.t_ = TS_it->first;
+    cur_.ts_left = TS_it->second.left.data();
+    if (ESVO_System_Status_ == "INITIALIZATION" && ets_ == IDLE) cur_.tr_ = ref_.tr_;
+    if (ESVO_System_Status_ == "WORKING" || (ESVO_System_Status_ == "INITIALIZATION" && ets_ == WORKING)) cur_.tr_ = T_world_cur_;
+    const size_t ev_cur = lower_bound_ev(cur_.t_);
+    cur_.numEventsSinceLastObs_ = ev_cur - ev_last + 1;
+    return true;
+  }
+  // ---- one pass of TrackingLoop's body (:84-171).  Returns true when a pose was produced (then also in T_world_cur_). ----
+  bool TrackingLoopOnce() {
+    if (refPCMap_.size() < 1 || TS_history_.size() < 1) return false;                       // keep idling
+    if (ESVO_System_Status_ == "INITIALIZATION" && ets_ == WORKING) { reset(); return false; }
+    if (ESVO_System_Status_ == "TERMINATE") return false;
+    if (frontend::toSec(ref_.t_) < frontend::toSec(refPCMap_.rbegin()->first))            // new reference map arrived
+      if (!refDataTransferring()) return false;
+    if (frontend::toSec(cur_.t_) < frontend::toSec(TS_history_.rbegin()->first)) {          // new observation arrived
+      if (frontend::toSec(ref_.t_) >= frontend::toSec(TS_history_.rbegin()->first)) return false;   // obs must come after the ref (reference: exit(-1))
+      if (!curDataTransferring()) return false;
+    } else return false;
+    if (rpSolver_.resetRegProblem(&ref_, &cur_)) {
+      if (ets_ == IDLE) ets_ = WORKING;
+      if (ESVO_System_Status_ != "WORKING") ESVO_System_Status_ = "WORKING";
+      const bool ok = rpType_ == core::REG_NUMERICAL ? rpSolver_.solve_numerical() : rpSolver_.solve_analytical();
+      if (!ok) return false;
+      T_world_cur_ = cur_.tr_;
+      lTimestamp_.push_back(cur_.t_); lPose_.push_back(cur_.tr_);                             // publishPose / saveTrajectory payload
+      return true;
+    }
+    ESVO_System_Status_ = "INITIALIZATION";
+    ets_ = IDLE;
+    return false;
+  }
+  void reset() { ets_ = IDLE; TS_id_ = 0; TS_history_.clear(); refPCMap_.clear(); events_left_.clear(); }   // (:247-255)
+
+  std::string ESVO_System_Status_ = "INITIALIZATION";   // the /ESVO_SYSTEM_STATUS parameter
+  TrackingStatus ets_ = IDLE;
+  core::RefFrame ref_;
+  core::CurFrame cur_;
+  esvo::Pose T_world_cur_;
+  std::vector<int64_t> lTimestamp_;
+  std::vector<esvo::Pose> lPose_;
+  core::RegProblemSolverLM rpSolver_;
+ private:
+  size_t lower_bound_ev(int64_t t) const {   // tools::EventBuffer_lower_bound (utils.h:50-55)
+    size_t lo = 0, hi = events_left_.size();
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (events_left_[mid].ts < t) lo = mid + 1; else hi = mid; }
+    return lo;
+  }
+  struct TsEntry { std::vector<uint8_t> left; size_t id; };
+  esvo::CameraSystem::Ptr cs_;
+  core::RegProblemType rpType_;
+  size_t TS_HISTORY_LENGTH_, REF_HISTORY_LENGTH_, TS_id_ = 0;
+  std::map<int64_t, std::shared_ptr<std::vector<float>>> refPCMap_;
+  std::map<int64_t, TsEntry> TS_history_;
+  std::deque<esvo::Event> events_left_;
+  PoseProvider getPoseAt_;
 };
 }  // namespace esvo_core

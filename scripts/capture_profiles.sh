@@ -1,12 +1,15 @@
 #!/bin/bash
-# Round-end evidence run on the GPU box: default bench, reference arm, launch list and one full ncu capture.
-# Artefacts land in gpurun_out/; scripts/summarize_ncu.py turns them into profiles/<tag>_*.md here.
+# Evidence run on the GPU box (round 2): launch list and `ncu --set full` captures at HEAD.
+# Artefacts land in gpurun_out/; scripts/summarize_ncu.py + scripts/ncu_lm_counters.py turn them into profiles/r2_* here.
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -2 gpurun_out/bench_final.err
-timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_final_ref.json 2>> gpurun_out/bench_final.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1100 -c 400 --csv --log-file gpurun_out/launches_final.csv \
-    python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"lm_kernel|bm_kernel|fuse_fold_kernel|ts_decay_median|fuse_stage|ts_ingest|map_regularize_kernel|seeds_order|points_order" \
-    -s 385 -c 11 -f -o gpurun_out/prof_final python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log
+B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-parity --no-extras --min-timed-s 0.001"
+# (1) launch list: one timed region (20 steps x 22 launches) behind priming (20) + profiled pass (20) + warm-up (5) steps
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1000 -c 440 --csv --log-file gpurun_out/launches_r2.csv $B > gpurun_out/ncu_launches_r2.log 2>&1
+# (2) full capture of one frame's kernels (16 matching launches per frame; skip 30 frames)
+timeout 1200 ncu --set full --clock-control none --import-source on \
+    -k regex:"lm2_kernel|bm_kernel|fuse_fold_kernel|fuse_stage_kernel|seeds_order|points_order|map_regularize_kernel|map_commit|ts_decay_median|ts_ingest|ts_remap|ts_scatter_fix" \
+    -s 480 -c 16 -f -o gpurun_out/prof_r2 $B > gpurun_out/ncu_full_r2.log 2>&1
+tail -2 gpurun_out/ncu_full_r2.log
+# (3) the LM kernel saturated (16 frames' seeds in one launch: no tail), same kernel as (2)
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:lm2_kernel -s 5 -c 1 -f -o gpurun_out/lm_sat_r2 python scripts/lm_saturation.py --child 12011 > gpurun_out/ncu_lm_sat_r2.log 2>&1
+tail -2 gpurun_out/ncu_lm_sat_r2.log

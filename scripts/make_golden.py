@@ -37,7 +37,8 @@ def small_rig():
 def main():
     os.makedirs(OUT, exist_ok=True)
     configs.RIGS["golden_small"] = small_rig()
-    lib = capi.load_oracle()
+    from oracle.loader import load_oracle
+    lib = load_oracle()
     l, r = configs.rig_calibs("golden_small")
     p = configs.params_for("hkust", lib)
     p.max_num_fusion_frames = 2
@@ -100,7 +101,8 @@ def extras():
     import cv2
     z = np.load(os.path.join(OUT, "small_rig_frame.npz"), allow_pickle=False)
     configs.RIGS["golden_small"] = ast.literal_eval(bytes(z["rig_json"]).decode())
-    lib = capi.load_oracle()
+    from oracle.loader import load_oracle
+    lib = load_oracle()
     l, r = configs.rig_calibs("golden_small")
 
     def backend(tweak=None):

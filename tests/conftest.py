@@ -15,10 +15,10 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def oracle_lib():
     """CPU oracle (test infrastructure).  Built on demand with `make -C oracle`."""
-    from esvo_b200 import capi
-    if not os.path.exists(capi.ORACLE_LIB):
+    from oracle import loader
+    if not os.path.exists(loader.ORACLE_LIB):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
-    return capi.load_oracle()
+    return loader.load_oracle()
 
 
 @pytest.fixture(scope="session")

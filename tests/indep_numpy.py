@@ -240,3 +240,52 @@ def track_jacobian(pts, R_, t_, Pl, mask, d_du, d_dv):
         dT[:, 0:3] = p[0] * np.eye(3); dT[:, 3:6] = p[1] * np.eye(3); dT[:, 6:9] = p[2] * np.eye(3); dT[:, 9:12] = np.eye(3)
         blk[i] = g @ dPi @ Jc @ dPi @ dT * p[2]
     return -blk @ JG0
+
+
+# ---- event front-end of esvo_Mapping::dataTransferring (esvo_core/src/esvo_Mapping.cpp:536-603), host logic ----
+def ros_to_sec(ns):
+    """ros::Time::toSec(): sec + 1e-9 * nsec."""
+    s, n = divmod(int(ns), 1000000000)
+    return float(s) + 1e-9 * float(n)
+
+
+def ros_from_sec(t):
+    """ros::Time(double): sec = floor(t), nsec = round((t - sec) * 1e9), normalised."""
+    sec = int(np.floor(t))
+    nsec = int(np.round((t - sec) * 1e9))
+    sec += nsec // 1000000000
+    nsec %= 1000000000
+    return sec * 1000000000 + nsec
+
+
+def select_close_events(t_events, t_end_ns, half_slice, process_event_num):
+    """Indices of the events dataTransferring selects (:562-575): walk back from lower_bound(t_end) until lower_bound(t_begin)
+    or PROCESS_EVENT_NUM pushes.  When no event is at/after t_end the reference's first push reads the slot one past the newest
+    event (deque::end()); that slot is skipped here but still counts against PROCESS_EVENT_NUM (include/esvo_b200/esvo_core.hpp)."""
+    t_events = np.asarray(t_events, np.int64)
+    t_begin_ns = ros_from_sec(max(0.0, ros_to_sec(t_end_ns) - 10 * half_slice))
+    ev_end = int(np.searchsorted(t_events, t_end_ns, side="left"))
+    ev_begin = int(np.searchsorted(t_events, t_begin_ns, side="left"))
+    out, budget = [], process_event_num
+    if ev_end == t_events.size and ev_end != ev_begin and budget > 0:
+        ev_end -= 1; budget -= 1
+    while ev_end != ev_begin and len(out) < budget:
+        out.append(ev_end); ev_end -= 1
+    return np.array(out, np.int64)
+
+
+def sample_pose_stamps(t_end_ns, half_slice):
+    """Virtual-view stamps of st_map_ (:585-599): t_begin, then t <- Time(t.toSec() + 0.05 * BM_half_slice_thickness) while <= t_end."""
+    t_end = ros_to_sec(t_end_ns)
+    t = ros_from_sec(max(0.0, t_end - 10 * half_slice))
+    out = []
+    while ros_to_sec(t) <= t_end:
+        out.append(t)
+        t = ros_from_sec(ros_to_sec(t) + 0.05 * half_slice)
+    return np.array(out, np.int64)
+
+
+def pack_point_cloud(p_cam, T_world_frame):
+    """publishPointCloud (:909-953): p_world = R p_cam + t as pcl::PointXYZ (f32), DepthMap iteration order."""
+    T = np.asarray(T_world_frame, float).reshape(4, 4)
+    return (np.asarray(p_cam) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)

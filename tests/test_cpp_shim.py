@@ -51,3 +51,83 @@ def test_pipelined_c_abi_example_compiles(product_lib, tmp_path):
         return
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 2 and "no CPU fallback" in p.stdout
+
+
+@pytest.mark.gpu
+def test_shim_mapping_to_tracking_matches_oracle(oracle_lib, product_lib, tmp_path):
+    """examples/shim_loop.cpp: dataTransferring helpers -> esvo_Mapping::MappingAtTime -> packPointCloud -> esvo_Tracking
+    (refMapCallback / timeSurfaceCallback / eventsCallback / TrackingLoopOnce) through the C++ shim on the GPU, against the same
+    sequence on the oracle with the front-end restated in Python from the reference (tests/indep_numpy.py)."""
+    import struct
+    import numpy as np
+    import indep_numpy as ind
+    from esvo_b200 import capi, configs, synth
+    build = os.path.join(ROOT, "esvo_b200", "_build")
+    exe = str(tmp_path / "shim_loop")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "shim_loop.cpp"),
+                           "-L" + build, "-lesvo_b200", "-Wl,-rpath," + build, "-o", exe])
+    s = synth.make_stream("hkust", seed=2, n_seeds=5000, t_ts=0.5)
+    s2 = synth.make_stream("hkust", seed=2, n_seeds=100, t_ts=0.51)
+    l, r = configs.rig_calibs("hkust")
+    o = capi.Backend(oracle_lib, l, r, configs.params_for("hkust", oracle_lib))
+    for cam, side in ((0, "left"), (1, "right")):
+        e = s[side]; o.ts_push_events(cam, e["x"], e["y"], e["t"], e["p"])
+    _, tl = o.ts_build(0, s["t_ts_ns"], want_idx=False); _, tr = o.ts_build(1, s["t_ts_ns"], want_idx=False)
+    o.ts_reset(0)
+    e2 = s2["left"]; o.ts_push_events(0, e2["x"], e2["y"], e2["t"], e2["p"])
+    _, tc = o.ts_build(0, s2["t_ts_ns"], want_idx=False)
+    W, H = o.W, o.H
+    half_slice, pen = 0.001, 5000
+    L = s["left"]
+    Tw = np.ascontiguousarray(s["T_world_left"], np.float64)
+    scen = tmp_path / "scen.bin"; resf = tmp_path / "res.bin"
+    with open(scen, "wb") as f:
+        f.write(struct.pack("<iii", W, H, 0)); f.write(struct.pack("<qq", s["t_ts_ns"], s2["t_ts_ns"])); f.write(Tw.tobytes())
+        f.write(struct.pack("<d", half_slice)); f.write(struct.pack("<ii", pen, L["x"].size))
+        for a, dt in ((L["x"], np.uint16), (L["y"], np.uint16), (L["t"], np.int64), (L["p"], np.uint8)):
+            f.write(np.ascontiguousarray(a, dt).tobytes())
+        f.write(tl.tobytes()); f.write(tr.tobytes()); f.write(tc.tobytes())
+        f.write(struct.pack("<i", s["pose_t"].size)); f.write(np.ascontiguousarray(s["pose_t"], np.int64).tobytes())
+        f.write(np.ascontiguousarray(s["poses"], np.float64).tobytes())
+    p = subprocess.run([exe, str(scen), str(resf)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    raw = open(resf, "rb").read()
+    hdr = np.frombuffer(raw, np.int32, 8); off = 32
+    ctr = np.frombuffer(raw, np.uint64, 8, off); off += 64
+    T_idle = np.frombuffer(raw, np.float64, 16, off).reshape(4, 4); off += 128
+    T_work = np.frombuffer(raw, np.float64, 16, off).reshape(4, 4); off += 128
+    sel = np.frombuffer(raw, np.int64, hdr[0], off); off += 8 * hdr[0]
+    stamps = np.frombuffer(raw, np.int64, hdr[1], off); off += 8 * hdr[1]
+    cloud = np.frombuffer(raw, np.float32, 3 * hdr[3], off).reshape(-1, 3)
+    # ---- the same sequence on the oracle, front-end restated from the reference ----
+    sel_ref = ind.select_close_events(L["t"], s["t_ts_ns"], half_slice, pen)
+    assert np.array_equal(sel, sel_ref) and sel.size == pen - 1          # observation stamp newer than every event: one budget slot skipped
+    st_ref = ind.sample_pose_stamps(s["t_ts_ns"], half_slice)
+    idx = np.searchsorted(s["pose_t"], st_ref, side="left")
+    keep = idx < s["pose_t"].size
+    assert np.array_equal(stamps, st_ref[keep])
+    poses = s["poses"][idx[keep]]
+    o.set_ts_pair(tl, tr, Tw)
+    co = o.mapping_at_time(L["x"][sel], L["y"][sel], L["t"][sel], st_ref[keep], poses)
+    assert [int(v) for v in ctr] == [co[k] for k in ("n_events", "n_seeds", "n_solved", "n_culled", "n_fusions", "bm_evals", "lm_evals", "map_size")][:8] or \
+        [int(v) for v in ctr[:6]] == [co[k] for k in ("n_events", "n_seeds", "n_solved", "n_culled", "n_fusions", "bm_evals")]
+    mo = o.map_download()
+    assert hdr[2] == mo.size and hdr[3] == mo.size
+    cloud_ref = ind.pack_point_cloud(mo["p_cam"], Tw)
+    rel = np.linalg.norm(cloud - cloud_ref, axis=1) / np.linalg.norm(cloud_ref, axis=1)
+    assert (rel < 1e-5).mean() > 0.999, rel.max()
+    # tracking, node already WORKING: reference pose = pose at the map stamp, prior = last tracked pose (= T here)
+    assert hdr[5] == 1
+    c = cloud.copy(); o.track_srand(1)
+    assert o.track_reset(c, Tw, Tw, tc) == 0
+    To, st = o.track_solve(True)
+    assert hdr[7] == st["n_iter"]
+    assert np.abs(T_work - To).max() < 1e-6, np.abs(T_work - To).max()
+    # node in INITIALIZATION / IDLE: reference pose = identity, prior = reference pose (esvo_Tracking.cpp:183-184,228-233)
+    assert hdr[4] == 1
+    c = cloud.copy(); o.track_srand(1)
+    o.track_reset(c, np.eye(4), np.eye(4), tc)
+    To2, _ = o.track_solve(True)
+    assert np.abs(T_idle - To2).max() < 1e-6
+    # numEventsSinceLastObs_ = distance(lower_bound(old cur stamp = 0), lower_bound(t_cur)) + 1 (:241-243)
+    assert hdr[6] == int(np.searchsorted(L["t"], s2["t_ts_ns"], side="left")) + 1

@@ -1,6 +1,7 @@
-"""BASELINE.json's full sizes on the GPU, checked through size-independent properties (the oracle would take
-minutes at these sizes): determinism / idempotence, range and ordering invariants, pipeline-depth invariance,
-and the Mapping -> Tracking loop (configs[3]) against the oracle on a short synthetic trajectory."""
+"""BASELINE.json's full sizes on the GPU: the BENCHMARKED configurations against the oracle (configs[1]: 5 000 events per
+frame, 20-frame fusion window, 25 frames; configs[2]: dsec 20 000 events, fusion_radius 1, SmoothTimeSurface, 5-frame window,
+7 frames -- bench.parity_block, the same code that fills BENCH.parity), plus size-independent properties: determinism /
+idempotence, range and ordering invariants, pipeline-depth invariance, and the Mapping -> Tracking loop (configs[3])."""
 import ctypes as C
 
 import numpy as np
@@ -29,6 +30,45 @@ def _frame(g, s):
     sd = s["seeds"]
     c = g.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
     return c, g.map_download()
+
+
+def _assert_parity(par):
+    assert par["idx_grid_equal"] and par["ts_bytes_equal"] and par["ts_mismatching_pixels"] == 0          # bit-exact integer work
+    assert par["accept_set_symmetric_difference"] == 0 and par["disparity_mismatches"] == 0 and par["seeds_compared"] > 0
+    assert par["lm_accept_symmetric_difference"] == 0 and par["lm_points_compared"] > 0
+    assert par["counters_equal"] and par["map_size_equal"] and par["map_order_equal"] and par["map_checksum_equal"]
+    # inverse depth: 1e-4 relative is the north star's tolerance.  The forward-difference LM amplifies rounding differences
+    # into different termination points for a handful of flat problems, so the bound is on the mean and on the fraction
+    assert par["inv_depth_l1"] <= 1e-6 and par["inv_depth_frac_above_1e-4"] <= 1e-3, par
+    assert par["map_inv_depth_l1"] <= 1e-6 and par["map_inv_depth_frac_above_1e-4"] <= 1e-3, par
+
+
+def test_cfg2_benchmarked_configuration_matches_oracle(product_lib):
+    """BASELINE configs[1] exactly as bench.py runs it: 5 000 events per frame, 20-frame window primed, then 5 consecutive
+    frames (25 in total) compared stage by stage; then the tracker on the last fused map (configs[3], tracking_hkust.yaml)."""
+    import bench
+    base = bench.make_workload(seed=10)
+    assert base["seeds"]["x"].size == 5000
+    par, trk = bench.parity_block(product_lib, base, "hkust", n_check=5, tracking=True)
+    print("cfg2 parity:", par)
+    assert par["frames_primed"] == 20 and par["frames_checked"] == 5
+    _assert_parity(par)
+    assert trk["ts_equal"]
+    for mode in ("analytical", "numerical"):
+        t = trk[mode]
+        assert t["stats_equal"] and t["pose_max_abs_diff_vs_oracle"] < 1e-6 and t["translation_rel_diff_vs_oracle"] < 1e-4, t
+
+
+def test_cfg3_dsec_benchmarked_configuration_matches_oracle(product_lib):
+    """SURVEY 8d cfg 3: 640x480 dsec rig, 20 000 events, disparity [0, 80], fusion_radius 1, SmoothTimeSurface, 5-frame window
+    (mapping_dsec.yaml): window primed with 5 frames, 2 more compared."""
+    import bench
+    base = bench.make_workload(seed=3, cfg="cfg3")
+    assert base["seeds"]["x"].size == 20000
+    par, _ = bench.parity_block(product_lib, base, "dsec", n_check=2, tracking=False)
+    print("cfg3 parity:", par)
+    assert par["frames_primed"] == 5
+    _assert_parity(par)
 
 
 @pytest.mark.parametrize("rig,n_seeds", [("hkust", 5000), ("dsec", 20000)])

@@ -133,13 +133,10 @@ def test_block_matching_parity(oracle_lib, product_lib, rig):
     assert np.array_equal(so["x_left"], sg["x_left"])
     assert np.array_equal(so["t_ns"], sg["t_ns"])
     assert np.array_equal(so["T_world_virtual"], sg["T_world_virtual"])
-    same = so["disp"] == sg["disp"]
-    # integer disparities must agree except on numerical ties of the f64 cost (documented in DESIGN.md)
-    assert same.mean() > 0.999, f"{(~same).sum()} disparity mismatches"
-    assert np.abs(so["cost"][same] - sg["cost"][same]).max() < 1e-12
-    assert np.array_equal(so["inv_depth"][same], sg["inv_depth"][same])
-    if (~same).any():
-        assert np.abs(so["cost"][~same] - sg["cost"][~same]).max() < 1e-12
+    # integer work: the disparity must be EQUAL (a mismatch could only come from an exact tie of the f64 cost, DESIGN.md deviation 1)
+    assert np.array_equal(so["disp"], sg["disp"]), f"{(so['disp'] != sg['disp']).sum()} disparity mismatches"
+    assert np.abs(so["cost"] - sg["cost"]).max() < 1e-12
+    assert np.array_equal(so["inv_depth"], sg["inv_depth"]) and np.array_equal(so["x_right"], sg["x_right"])
 
 
 def test_block_matching_coarse_to_fine(oracle_lib, product_lib):
@@ -148,7 +145,7 @@ def test_block_matching_coarse_to_fine(oracle_lib, product_lib):
     s, o, g, so, sg, evo, evg = _bm_pair(oracle_lib, product_lib, "hkust", tweak=tw)
     assert so.size > 50 and evo == evg and so.size == sg.size
     assert np.array_equal(so["x_left_raw"], sg["x_left_raw"])
-    assert (so["disp"] == sg["disp"]).mean() > 0.999
+    assert np.array_equal(so["disp"], sg["disp"])
 
 
 @pytest.mark.parametrize("rig,lsnorm", [("hkust", capi.LSNORM_TDIST), ("dsec", capi.LSNORM_TDIST),
@@ -164,7 +161,9 @@ def test_depth_solver_parity(oracle_lib, product_lib, rig, lsnorm):
     assert np.array_equal(po["x"], pg["x"]) and np.array_equal(po["row"], pg["row"]) and np.array_equal(po["col"], pg["col"])
     r = rel(pg["inv_depth"], po["inv_depth"])
     print(f"[{rig}/{lsnorm}] n={po.size} rho rel err: max {r.max():.3e} median {np.median(r):.3e}; nfev oracle {evo} gpu {evg}")
-    assert (r < 1e-4).mean() > 0.995, f"{(r >= 1e-4).sum()} of {r.size} seeds beyond 1e-4"
+    w = int(np.argmax(r))
+    print(f"   worst seed #{w}: x_left {po['x'][w]}, rho oracle {po['inv_depth'][w]:.9g} gpu {pg['inv_depth'][w]:.9g}, cost {po['residual'][w]:.6g} / {pg['residual'][w]:.6g}")
+    assert (r < 1e-4).mean() >= 0.999, f"{(r >= 1e-4).sum()} of {r.size} seeds beyond 1e-4"
     assert np.median(r) < 1e-7   # forward-difference Jacobian noise: h = 1.5e-8*rho amplifies 1e-16 rounding
     ok = r < 1e-7
     if lsnorm != capi.LSNORM_ZNCC:   # the reference leaves result[1] uninitialised for "zncc" (DepthProblemSolver.cpp:199-211)
@@ -172,6 +171,33 @@ def test_depth_solver_parity(oracle_lib, product_lib, rig, lsnorm):
     assert rel(pg["residual"][ok], po["residual"][ok]).max() < 1e-4
     assert np.allclose(pg["p_cam"][ok], po["p_cam"][ok], rtol=1e-6, atol=1e-9)
     assert abs(evo - evg) <= 0.01 * evo
+
+
+def test_fusion_into_a_regularised_map(oracle_lib, product_lib):
+    """DepthPoint::update_studentT takes its "new point" branch for a map point whose inverse depth is invalid
+    (DepthPoint.cpp:181-187) -- reachable through the ABI: esvo_map_regularize marks rejected points with rho = -1, and a
+    later esvo_fuse(reset_map = 0) fuses into them."""
+    s, o, g, so, sg, _, _ = _bm_pair(oracle_lib, product_lib, "hkust")
+    po, _ = o.depth_solve(so)
+    T0 = s["T_world_left"].copy()
+    res = []
+    for be in (o, g):
+        be.fuse(po, T0, 0, True)
+        be.map_regularize()
+        m1 = be.map_download()
+        nf = be.fuse(po[::2], T0, 0, False)            # second round into the regularised map, no reset
+        res.append((m1, nf, be.map_download()))
+    (a1, nfa, a2), (b1, nfb, b2) = res
+    assert (a1["inv_depth"] <= -1e-6).sum() > 10, "the scenario must contain regularisation-rejected points"
+    assert a1.size == b1.size and np.array_equal(a1["inv_depth"] > -1e-6, b1["inv_depth"] > -1e-6)
+    assert nfa == nfb and a2.size == b2.size
+    assert np.array_equal(a2["row"], b2["row"]) and np.array_equal(a2["col"], b2["col"]) and np.array_equal(a2["age"], b2["age"])
+    v = a2["inv_depth"] > -1e-6
+    assert np.array_equal(v, b2["inv_depth"] > -1e-6)
+    for name in ("inv_depth", "scale2", "nu", "variance", "residual"):
+        assert rel(b2[name][v], a2[name][v]).max() < 1e-9, name
+    # some of the rejected points were re-initialised by the second round (the branch under test)
+    assert ((a1["inv_depth"] <= -1e-6) & (a2["inv_depth"][:a1.size] > -1e-6)).sum() > 0
 
 
 @pytest.mark.parametrize("rig", ["hkust", "dsec"])

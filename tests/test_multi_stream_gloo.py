@@ -16,7 +16,8 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     from esvo_b200 import capi, configs, dist as edist, synth
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lib = capi.load_oracle()
+    from oracle.loader import load_oracle
+    lib = load_oracle()
     seed = edist.stream_seed(rank)
     s = synth.make_stream("hkust", seed=seed, n_seeds=200, n_segments=40, history_ms=30.0)
     l, r = configs.rig_calibs("hkust")
