@@ -147,9 +147,123 @@ __global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, Pose16 Tfw, int rad
 // ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
 // NAIVE = DepthFusion::naive_propagation (:232-288): same ordered replay, but nearest-wins instead of fusion.
 struct CleanArgs { int enable; double var_thr, age_thr, rmax, rmin; };
-// One thread per ACTIVE pixel (dense: the list holds exactly the pixels with a non-empty contribution list), so a warp
-// carries 32 replays instead of the 1-3 a thread-per-image-pixel launch would (the fold's cost in the frame pipeline is
-// warp-slot time, not instructions: profiles/r2_*).
+
+// ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
+// The state of one map pixel while its contribution list is replayed.
+struct FoldState {
+  bool ex;
+  double rho, s2, nu, var, res, x0, x1, pc0, pc1, pc2;
+  long long age;
+  int erow, ecol;
+  unsigned long long fkey;
+  int nfus;
+  // p_cam is overwritten by every create / fuse step and never read back by the recurrence, so it is evaluated once at the
+  // end from the inverse depth that set it last (pc_rho); a replacement copies the propagated p_cam.
+  bool pc_pending;
+  double pc_rho;
+  double sdm;          // 2*sqrt(var) of the map point, refreshed whenever var changes
+};
+__device__ __forceinline__ void fold_load(const MapSoA& M, int pix, int row, int col, FoldState& f) {
+  f.ex = M.exists[pix] != 0;
+  f.rho = f.s2 = f.nu = f.var = f.res = f.x0 = f.x1 = f.pc0 = f.pc1 = f.pc2 = 0;
+  f.age = 0; f.erow = row; f.ecol = col; f.fkey = 0; f.nfus = 0; f.pc_pending = false; f.pc_rho = 0;
+  if (f.ex) {
+    f.rho = M.rho[pix]; f.s2 = M.s2[pix]; f.nu = M.nu[pix]; f.var = M.var[pix]; f.res = M.res[pix]; f.x0 = M.x0[pix]; f.x1 = M.x1[pix];
+    f.pc0 = M.pc0[pix]; f.pc1 = M.pc1[pix]; f.pc2 = M.pc2[pix]; f.age = M.age[pix]; f.erow = M.row[pix]; f.ecol = M.col[pix];
+    f.fkey = M.first_key[pix];
+  }
+  f.sdm = f.ex ? 2 * sqrt(f.var) : 0.0;
+}
+// NAIVE = DepthFusion::naive_propagation (:232-288): same ordered replay, but nearest-wins instead of fusion.
+template <bool NAIVE>
+__device__ __forceinline__ void fold_apply(const DevConsts& dc, const PropSoA& P, FoldState& f, int row, int col, int cid, const FoldRec& r,
+                                           unsigned long long seq_base) {
+  const int sid = cid / 9;
+  const double prho = r.rho, ps2 = r.s2, pnu = r.nu, pvar = r.var, pres = r.res;
+  if (!f.ex) {  // case 1 (:126-145)
+    f.ex = true; f.erow = row; f.ecol = col; f.x0 = col + 0.5; f.x1 = row + 0.5;
+    f.rho = prho; f.var = pvar; f.s2 = ps2; f.nu = pnu;
+    if (dc.lsnorm == ESVO_LSNORM_L2 && f.var < 1e-6) f.var = 1e-6;
+    f.sdm = (dc.lsnorm == ESVO_LSNORM_L2) ? 2 * sqrt(f.var) : r.sd2;
+    f.res = pres; f.age = P.age[sid];
+    f.pc_rho = prho; f.pc_pending = true;
+    f.fkey = seq_base + (unsigned long long)cid;
+    if (NAIVE) { f.s2 = 0; f.nu = 0; }               // dp_new.update(): the Gaussian fields only
+    return;
+  }
+  if (NAIVE) {                                       // case 2 of naive_propagation (:274-283)
+    if (f.rho > prho) return;                        // the propagated point is farther
+    if (pres < f.res) {                              // dm->get(row,col) = dp_prop
+      f.rho = prho; f.s2 = ps2; f.nu = pnu; f.var = pvar; f.res = pres; f.age = P.age[sid];
+      f.sdm = r.sd2;
+      f.x0 = P.x0[sid]; f.x1 = P.x1[sid]; f.pc0 = P.pc0[sid]; f.pc1 = P.pc1[sid]; f.pc2 = P.pc2[sid];
+      f.pc_pending = false;
+      f.erow = P.row[sid]; f.ecol = P.col[sid];
+    }
+    return;
+  }
+  bool compat;
+  if (dc.lsnorm == ESVO_LSNORM_L2) {
+    const double d2 = (prho - f.rho) * (prho - f.rho);
+    compat = (d2 / pvar + d2 / f.var) < 5.99;
+  } else {
+    const double diff = fabs(prho - f.rho);
+    compat = diff < r.sd2 || diff < f.sdm;
+  }
+  if (compat) {  // case 2.1 (:162-177)
+    if (!(f.rho > -1e-6)) {
+      // DepthPoint::update / update_studentT take their "new point" branch for a map point that carries no valid inverse
+      // depth (DepthPoint.cpp:158-163,181-187): overwrite, no inner age_++
+      f.rho = prho; f.var = pvar; f.s2 = ps2; f.nu = pnu;
+      if (dc.lsnorm == ESVO_LSNORM_L2 && f.var < 1e-6) f.var = 1e-6;
+    } else if (dc.lsnorm == ESVO_LSNORM_L2) {
+      const double t = f.rho;
+      f.rho = (f.var * prho + pvar * t) / (f.var + pvar);
+      const double tv = f.var;
+      f.var = (tv * pvar) / (tv + pvar);
+      if (f.var < 1e-6) f.var = 1e-6;
+    } else {
+      const double nu_u = fmin(pnu, f.nu);
+      const double rho_u = (ps2 * f.rho + f.s2 * prho) / (f.s2 + ps2);
+      const double dd = f.rho - prho;
+      const double s2_u = (nu_u + (dd * dd) / (f.s2 + ps2)) / (nu_u + 1) * (f.s2 * ps2) / (f.s2 + ps2);
+      f.rho = rho_u; f.s2 = s2_u; f.nu = nu_u + 1;
+      f.var = f.nu / (f.nu - 2) * f.s2;
+      f.age++;                                   // DepthPoint.cpp:179
+    }
+    f.sdm = 2 * sqrt(f.var);
+    f.age++;                                     // DepthFusion.cpp:171
+    f.res = fmin(f.res, pres);
+    f.pc_rho = prho; f.pc_pending = true;        // p_cam from the PROPAGATED rho (:174)
+    f.nfus++;
+  } else {       // case 2.2 (:178-188)
+    if (f.rho - f.sdm > prho) return;
+    if (pvar < f.var && pres < f.res) {              // dm->get(row,col) = dp_prop
+      f.rho = prho; f.s2 = ps2; f.nu = pnu; f.var = pvar; f.res = pres; f.age = P.age[sid];
+      f.sdm = r.sd2;
+      f.x0 = P.x0[sid]; f.x1 = P.x1[sid]; f.pc0 = P.pc0[sid]; f.pc1 = P.pc1[sid]; f.pc2 = P.pc2[sid];
+      f.pc_pending = false;
+      f.erow = P.row[sid]; f.ecol = P.col[sid];
+    }
+  }
+}
+__device__ __forceinline__ void fold_store(const DevConsts& dc, MapSoA& M, int pix, FoldState& f, const CleanArgs& clean, uint32_t* cbits,
+                                           unsigned long long seq_base, unsigned long long* scal) {
+  if (f.pc_pending) cam2world_f(dc, f.x0, f.x1, f.pc_rho, f.pc0, f.pc1, f.pc2);
+  // SmartGrid::clean (:222-243) right behind the fusion of the whole window (esvo_Mapping.cpp:385-386): the pixel's final state
+  // is at hand, so the predicate is applied here instead of in a pass over the image
+  if (clean.enable && f.ex && !(f.rho > -1e-6 && (double)f.age >= clean.age_thr && f.var <= clean.var_thr && f.rho <= clean.rmax && f.rho >= clean.rmin))
+    f.ex = false;
+  // creator bit of the surviving element: rank in the element list = number of set bits below it (map_gather_list_kernel)
+  if (f.ex && cbits && f.fkey >= seq_base) { const unsigned long long cc = f.fkey - seq_base; atomicOr(&cbits[cc >> 5], 1u << (cc & 31)); }
+  M.exists[pix] = f.ex ? 1 : 0;
+  M.rho[pix] = f.rho; M.s2[pix] = f.s2; M.nu[pix] = f.nu; M.var[pix] = f.var; M.res[pix] = f.res; M.x0[pix] = f.x0; M.x1[pix] = f.x1;
+  M.pc0[pix] = f.pc0; M.pc1[pix] = f.pc1; M.pc2[pix] = f.pc2; M.age[pix] = f.age; M.row[pix] = f.erow; M.col[pix] = f.ecol;
+  M.first_key[pix] = f.fkey;
+  if (f.nfus) atomicAdd(&scal[0], (unsigned long long)f.nfus);
+}
+
+// Thread-per-active-pixel form (dense over the active list): the production form (see fuse_finish for the measurement).
 template <bool NAIVE>
 __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* head, const int32_t* __restrict__ next,
                                  const int32_t* __restrict__ active, unsigned long long seq_base, unsigned long long* scal,
@@ -166,91 +280,8 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
   int cnt = 0, total = 0;
   for (int q = h; q >= 0; q = next[q]) { if (cnt < CAP) ids[cnt++] = q; ++total; }
   const int row = pix / dc.W, col = pix - row * dc.W;
-  bool ex = M.exists[pix] != 0;
-  double rho = 0, s2 = 0, nu = 0, var = 0, res = 0, x0 = 0, x1 = 0, pc0 = 0, pc1 = 0, pc2 = 0;
-  long long age = 0; int erow = row, ecol = col;
-  unsigned long long fkey = 0;
-  if (ex) {
-    rho = M.rho[pix]; s2 = M.s2[pix]; nu = M.nu[pix]; var = M.var[pix]; res = M.res[pix]; x0 = M.x0[pix]; x1 = M.x1[pix];
-    pc0 = M.pc0[pix]; pc1 = M.pc1[pix]; pc2 = M.pc2[pix]; age = M.age[pix]; erow = M.row[pix]; ecol = M.col[pix];
-    fkey = M.first_key[pix];
-  }
-  int nfus = 0;
-  // p_cam is overwritten by every create / fuse step and never read back by the recurrence, so it is evaluated
-  // once at the end from the inverse depth that set it last (pc_rho); a replacement copies the propagated p_cam.
-  bool pc_pending = false;
-  double pc_rho = 0;
-  double sdm = ex ? 2 * sqrt(var) : 0.0;          // 2*sqrt(var) of the map point, refreshed whenever var changes
-  auto apply = [&](int cid, const FoldRec& r) {
-    const int sid = cid / 9;
-    const double prho = r.rho, ps2 = r.s2, pnu = r.nu, pvar = r.var, pres = r.res;
-    if (!ex) {  // case 1 (:126-145)
-      ex = true; erow = row; ecol = col; x0 = col + 0.5; x1 = row + 0.5;
-      rho = prho; var = pvar; s2 = ps2; nu = pnu;
-      if (dc.lsnorm == ESVO_LSNORM_L2 && var < 1e-6) var = 1e-6;
-      sdm = (dc.lsnorm == ESVO_LSNORM_L2) ? 2 * sqrt(var) : r.sd2;
-      res = pres; age = P.age[sid];
-      pc_rho = prho; pc_pending = true;
-      fkey = seq_base + (unsigned long long)cid;
-      if (NAIVE) { s2 = 0; nu = 0; }               // dp_new.update(): the Gaussian fields only
-      return;
-    }
-    if (NAIVE) {                                   // case 2 of naive_propagation (:274-283)
-      if (rho > prho) return;                      // the propagated point is farther
-      if (pres < res) {                            // dm->get(row,col) = dp_prop
-        rho = prho; s2 = ps2; nu = pnu; var = pvar; res = pres; age = P.age[sid];
-        sdm = r.sd2;
-        x0 = P.x0[sid]; x1 = P.x1[sid]; pc0 = P.pc0[sid]; pc1 = P.pc1[sid]; pc2 = P.pc2[sid];
-        pc_pending = false;
-        erow = P.row[sid]; ecol = P.col[sid];
-      }
-      return;
-    }
-    bool compat;
-    if (dc.lsnorm == ESVO_LSNORM_L2) {
-      const double d2 = (prho - rho) * (prho - rho);
-      compat = (d2 / pvar + d2 / var) < 5.99;
-    } else {
-      const double diff = fabs(prho - rho);
-      compat = diff < r.sd2 || diff < sdm;
-    }
-    if (compat) {  // case 2.1 (:162-177)
-      if (!(rho > -1e-6)) {
-        // DepthPoint::update / update_studentT take their "new point" branch for a map point that carries no valid inverse
-        // depth (DepthPoint.cpp:158-163,181-187; e.g. one marked -1 by the regularisation): overwrite, no inner age_++
-        rho = prho; var = pvar; s2 = ps2; nu = pnu;
-        if (dc.lsnorm == ESVO_LSNORM_L2 && var < 1e-6) var = 1e-6;
-      } else if (dc.lsnorm == ESVO_LSNORM_L2) {
-        const double t = rho;
-        rho = (var * prho + pvar * t) / (var + pvar);
-        const double tv = var;
-        var = (tv * pvar) / (tv + pvar);
-        if (var < 1e-6) var = 1e-6;
-      } else {
-        const double nu_u = fmin(pnu, nu);
-        const double rho_u = (ps2 * rho + s2 * prho) / (s2 + ps2);
-        const double dd = rho - prho;
-        const double s2_u = (nu_u + (dd * dd) / (s2 + ps2)) / (nu_u + 1) * (s2 * ps2) / (s2 + ps2);
-        rho = rho_u; s2 = s2_u; nu = nu_u + 1;
-        var = nu / (nu - 2) * s2;
-        age++;                                   // DepthPoint.cpp:179
-      }
-      sdm = 2 * sqrt(var);
-      age++;                                     // DepthFusion.cpp:171
-      res = fmin(res, pres);
-      pc_rho = prho; pc_pending = true;          // p_cam from the PROPAGATED rho (:174)
-      nfus++;
-    } else {       // case 2.2 (:178-188)
-      if (rho - sdm > prho) return;
-      if (pvar < var && pres < res) {              // dm->get(row,col) = dp_prop
-        rho = prho; s2 = ps2; nu = pnu; var = pvar; res = pres; age = P.age[sid];
-        sdm = r.sd2;
-        x0 = P.x0[sid]; x1 = P.x1[sid]; pc0 = P.pc0[sid]; pc1 = P.pc1[sid]; pc2 = P.pc2[sid];
-        pc_pending = false;
-        erow = P.row[sid]; ecol = P.col[sid];
-      }
-    }
-  };
+  FoldState f;
+  fold_load(M, pix, row, col, f);
   if (total <= CAP) {
     if (cnt <= 16) {
       for (int a = 1; a < cnt; ++a) { int v = ids[a], b = a - 1; while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; } ids[b + 1] = v; }
@@ -273,7 +304,7 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
     for (int a = 0; a < cnt; ++a) {              // the next record is in flight while this one is folded
       FoldRec nxt = cur;
       if (a + 1 < cnt) nxt = P.hot[ids[a + 1] / 9];
-      apply(ids[a], cur);
+      fold_apply<NAIVE>(dc, P, f, row, col, ids[a], cur, seq_base);
       cur = nxt;
     }
   } else {  // long list: repeated minimum selection, O(L^2) walks, no storage
@@ -281,22 +312,82 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
     for (int a = 0; a < total; ++a) {
       int best = 0x7fffffff;
       for (int q = h; q >= 0; q = next[q]) if (q > last && q < best) best = q;
-      apply(best, P.hot[best / 9]);
+      fold_apply<NAIVE>(dc, P, f, row, col, best, P.hot[best / 9], seq_base);
       last = best;
     }
   }
-  if (pc_pending) cam2world_f(dc, x0, x1, pc_rho, pc0, pc1, pc2);
-  // SmartGrid::clean (:222-243) right behind the fusion of the whole window (esvo_Mapping.cpp:385-386): the thread holds the
-  // pixel's final state, so the predicate is applied here instead of in a pass over the image
-  if (clean.enable && ex && !(rho > -1e-6 && (double)age >= clean.age_thr && var <= clean.var_thr && rho <= clean.rmax && rho >= clean.rmin))
-    ex = false;
-  // creator bit of the surviving element: rank in the element list = number of set bits below it (map_gather_list_kernel)
-  if (ex && cbits && fkey >= seq_base) { const unsigned long long cc = fkey - seq_base; atomicOr(&cbits[cc >> 5], 1u << (cc & 31)); }
-  M.exists[pix] = ex ? 1 : 0;
-  M.rho[pix] = rho; M.s2[pix] = s2; M.nu[pix] = nu; M.var[pix] = var; M.res[pix] = res; M.x0[pix] = x0; M.x1[pix] = x1;
-  M.pc0[pix] = pc0; M.pc1[pix] = pc1; M.pc2[pix] = pc2; M.age[pix] = age; M.row[pix] = erow; M.col[pix] = ecol;
-  M.first_key[pix] = fkey;
-  if (nfus) atomicAdd(&scal[0], (unsigned long long)nfus);
+  fold_store(dc, M, pix, f, clean, cbits, seq_base, scal);
+}
+
+// Warp-per-active-pixel form (ESVO_FOLD_WARP=1): lower latency alone, more warp-slot time in the pipeline.  A pixel's replay is inherently serial (every step depends on the state the previous one
+// left), so the 32 lanes cannot share ONE replay -- but they can take everything around it: the contribution ids are rank-sorted
+// by all lanes in shared memory (no local-memory heap sort), the 48-byte records of the next 32 steps are fetched by 32 lanes
+// at once (one gather instead of 32 dependent loads) and broadcast step by step; the replay itself runs redundantly in every
+// lane (uniform control flow, lane 0 stores).  With one warp per pixel there are thousands of warps to hide the list walk and
+// the division chains of each other, where the thread form has ~1.5 warps per SM.
+constexpr int FOLD_CAPW = 256;        // ids per pixel held in shared memory; longer lists take the selection walk
+// FOLD_WPB warps per block.  One-warp blocks (4 K registers) slot into the holes single LM blocks leave in a busy SM; bigger
+// blocks wait for several neighbouring LM warps to retire (measured: 0.27 -> 0.32 ms/step with 4-warp blocks).
+template <bool NAIVE, int FOLD_WPB>
+__global__ void __launch_bounds__(FOLD_WPB * 32, 16 / FOLD_WPB) fuse_fold_warp_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* head,
+                                                                        const int32_t* __restrict__ next, const int32_t* __restrict__ active,
+                                                                        unsigned long long seq_base, unsigned long long* scal, uint32_t* cbits,
+                                                                        CleanArgs clean) {
+  __shared__ int s_ids[FOLD_WPB][FOLD_CAPW], s_sorted[FOLD_WPB][FOLD_CAPW];
+  const unsigned FULLM = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * FOLD_WPB;
+  const int n_active = (int)scal[3];
+  for (int t = blockIdx.x * FOLD_WPB + w; t < n_active; t += nwarps) {
+    const int pix = active[t];
+    int h = 0, total = 0;
+    if (lane == 0) {
+      h = head[pix];
+      if (h >= 0) {
+        head[pix] = -1;
+        for (int q = h; q >= 0; q = next[q]) { if (total < FOLD_CAPW) s_ids[w][total] = q; ++total; }   // serial list walk
+      }
+    }
+    h = __shfl_sync(FULLM, h, 0); total = __shfl_sync(FULLM, total, 0);
+    if (h < 0) continue;             // listed twice: the first copy folded it
+    __syncwarp();
+    const int row = pix / dc.W, col = pix - row * dc.W;
+    FoldState f;
+    fold_load(M, pix, row, col, f);
+    if (total <= FOLD_CAPW) {
+      // rank sort: ids are distinct, rank = number of smaller ids
+      for (int e = lane; e < total; e += 32) {
+        const int v = s_ids[w][e];
+        int rank = 0;
+        for (int k = 0; k < total; ++k) rank += s_ids[w][k] < v;
+        s_sorted[w][rank] = v;
+      }
+      __syncwarp();
+      FoldRec mine;                  // record of step base + lane, fetched one chunk ahead
+      { const int e = lane < total ? lane : 0; mine = P.hot[s_sorted[w][e] / 9]; }
+      for (int base = 0; base < total; base += 32) {
+        const FoldRec cur = mine;
+        if (base + 32 < total) { const int e = base + 32 + lane < total ? base + 32 + lane : base + 32; mine = P.hot[s_sorted[w][e] / 9]; }
+        const int nstep = min(32, total - base);
+        for (int k = 0; k < nstep; ++k) {
+          FoldRec r;
+          r.rho = __shfl_sync(FULLM, cur.rho, k); r.s2 = __shfl_sync(FULLM, cur.s2, k); r.nu = __shfl_sync(FULLM, cur.nu, k);
+          r.var = __shfl_sync(FULLM, cur.var, k); r.res = __shfl_sync(FULLM, cur.res, k); r.sd2 = __shfl_sync(FULLM, cur.sd2, k);
+          fold_apply<NAIVE>(dc, P, f, row, col, s_sorted[w][base + k], r, seq_base);
+        }
+      }
+    } else {   // very long list: repeated minimum selection over the list, every lane walks (uniform), no storage
+      int last = -1;
+      for (int a = 0; a < total; ++a) {
+        int best = 0x7fffffff;
+        for (int q = h; q >= 0; q = next[q]) if (q > last && q < best) best = q;
+        fold_apply<NAIVE>(dc, P, f, row, col, best, P.hot[best / 9], seq_base);
+        last = best;
+      }
+    }
+    if (lane == 0) fold_store(dc, M, pix, f, clean, cbits, seq_base, scal);
+    __syncwarp();
+  }
 }
 
 // ---- SmartGrid::clean (:222-243) ----
@@ -377,7 +468,7 @@ __global__ void map_regularize_kernel(DevConsts dc, MapSoA M, int radius, int mi
 // Student-t merge of the close neighbours (DepthRegularization.cpp:63-86: sequential, non-associative in floating point) is
 // replayed in raster order by broadcasting one close neighbour at a time.  Same arithmetic, same order as the thread form
 // above; what changes is the latency: 121 (r = 5) ... 1681 (r = 20) dependent neighbour visits become 4 ... 53 chunk loads.
-__global__ void __launch_bounds__(256) map_regularize_warp_kernel(DevConsts dc, MapSoA M, int radius, int min_nb, int min_close,
+__global__ void __launch_bounds__(256, 3) map_regularize_warp_kernel(DevConsts dc, MapSoA M, int radius, int min_nb, int min_close,
                                                                   const int32_t* __restrict__ active, const unsigned long long* __restrict__ scal) {
   const unsigned FULLM = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -854,10 +945,26 @@ int fuse_finish(Ctx* c, bool naive, const double* clean4) {
     cbits = ms->cbits;
   }
   // at most one thread per image pixel can be active; the grid covers that bound, surplus blocks exit on the device count
-  const int npix = c->dc.W * c->dc.H, B = 32;
-  const int bound = (int)std::min<size_t>((size_t)npix, ms->staged * 9);
-  if (naive) fuse_fold_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
-  else fuse_fold_kernel<false><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+  // Thread-per-active-pixel is the production form: in the frame pipeline the fold's cost is warp-slot time next to the LM
+  // blocks, and 219 dense warps x ~100 us beat 7 000 one-pixel warps x ~20 us (0.268 vs 0.314 ms/step, profiles/r2_sweeps.md),
+  // although the warp form is faster alone (169 vs 260 us).  ESVO_FOLD_WARP=1 selects the warp form (latency-critical use).
+  static const int warp_fold = getenv("ESVO_FOLD_WARP") ? atoi(getenv("ESVO_FOLD_WARP")) : 0;
+  if (!warp_fold) {
+    const int npix = c->dc.W * c->dc.H, B = 32;
+    const int bound = (int)std::min<size_t>((size_t)npix, ms->staged * 9);
+    if (naive) fuse_fold_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+    else fuse_fold_kernel<false><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+  } else {   // persistent: one-warp blocks walk the active list, one warp per pixel
+    static const int G = getenv("ESVO_DBG_FOLD_GRID") ? atoi(getenv("ESVO_DBG_FOLD_GRID")) : 148 * 16;
+    static const int wpb = getenv("ESVO_DBG_FOLD_WPB") ? atoi(getenv("ESVO_DBG_FOLD_WPB")) : 1;
+    if (wpb == 4) {
+      if (naive) fuse_fold_warp_kernel<true, 4><<<G, 128, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+      else fuse_fold_warp_kernel<false, 4><<<G, 128, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+    } else {
+      if (naive) fuse_fold_warp_kernel<true, 1><<<G, 32, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+      else fuse_fold_warp_kernel<false, 1><<<G, 32, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+    }
+  }
   c->launches += 1;
   ms->seq_base += (unsigned long long)ms->staged * 9ULL;
   ms->staged = 0;
@@ -884,9 +991,12 @@ int map_regularize(Ctx* c, bool count) {
     if (dbg_thread_form)
       map_regularize_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
                                                                         c->prm.reg_min_close_neighbours, ms->active, ms->d_scal);
-    else   // persistent: 148 SMs x 8 blocks of 8 warps walk the active list
-      map_regularize_warp_kernel<<<148 * 8, 256, 0, c->stream>>>(c->dc, ms->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
-                                                                c->prm.reg_min_close_neighbours, ms->active, ms->d_scal);
+    else {   // persistent: small blocks (see fuse_fold_warp_kernel) walk the active list, one warp per pixel
+      static const int G = getenv("ESVO_DBG_REG_GRID") ? atoi(getenv("ESVO_DBG_REG_GRID")) : 148 * 16;
+      static const int T = getenv("ESVO_DBG_REG_THREADS") ? atoi(getenv("ESVO_DBG_REG_THREADS")) : 32;
+      map_regularize_warp_kernel<<<G, T, 0, c->stream>>>(c->dc, ms->m, c->prm.reg_radius, c->prm.reg_min_neighbours,
+                                                         c->prm.reg_min_close_neighbours, ms->active, ms->d_scal);
+    }
     if (count) map_commit_count_list_kernel<<<div_up(bound, 256), 256, 0, c->stream>>>(ms->m, 1, ms->active, ms->d_scal);
     else map_regularize_commit_kernel<<<div_up(npix, 256), 256, 0, c->stream>>>(npix, ms->m);
     c->launches += 2;

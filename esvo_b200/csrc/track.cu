@@ -18,11 +18,13 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace esvo {
 
-constexpr int TRK_THREADS = 512;
+constexpr int TRK_THREADS = 256;   // 8 warps: the scalar trust-region algebra on thread 0 gets up to 255 registers (no spills in the unrolled qrsolv)
 constexpr int TRK_MAXB = 1024;
 
 struct TrkDev {
@@ -157,50 +159,79 @@ __device__ double det3_d(const double* A) {
 // ---------------------------------------------------------------------------------------------
 // n = 6 trust-region algebra on one thread (Eigen internal::qrsolv / lmpar2)
 // ---------------------------------------------------------------------------------------------
-__device__ void givens_d(double p, double q, double& c, double& s) {
+__device__ __forceinline__ void givens_d(double p, double q, double& c, double& s) {
+  // Eigen JacobiRotation::makeGivens (real).  The quotient and 1/sqrt(1+t^2) use the branch-free Newton forms of common.cuh
+  // (<= 1 ulp; t in [-1,1] so 1+t^2 is in [1,2]) unless the divisor is outside the range they cover: on one thread of a block
+  // that waits at a barrier, the latency of this chain (21 rotations per qrsolv, up to 10 qrsolv per lmpar) IS the solver's time.
   if (q == 0) { c = p < 0 ? -1 : 1; s = 0; }
   else if (p == 0) { c = 0; s = q < 0 ? 1 : -1; }
-  else if (fabs(p) > fabs(q)) { double t = q / p, u = sqrt(1 + t * t); if (p < 0) u = -u; c = 1 / u; s = -t * c; }
-  else { double t = p / q, u = sqrt(1 + t * t); if (q < 0) u = -u; s = -1 / u; c = -t * s; }
+  else if (fabs(p) > fabs(q)) {
+    if (fabs(p) > 1e-280 && fabs(p) < 1e280) { const double t = div_nr(q, p), r = rsqrt_nr(1 + t * t); c = p < 0 ? -r : r; s = -t * c; }
+    else { double t = q / p, u = sqrt(1 + t * t); if (p < 0) u = -u; c = 1 / u; s = -t * c; }
+  } else {
+    if (fabs(q) > 1e-280 && fabs(q) < 1e280) { const double t = div_nr(p, q), r = rsqrt_nr(1 + t * t); s = q < 0 ? r : -r; c = -t * s; }
+    else { double t = p / q, u = sqrt(1 + t * t); if (q < 0) u = -u; s = -1 / u; c = -t * s; }
+  }
 }
 __device__ double norm6(const double* v) { double s = 0; for (int i = 0; i < 6; ++i) s += v[i] * v[i]; return sqrt(s); }
 
-// s: 6x6 (row i, col j at s[j*6+i]); upper triangle = R
-__device__ void qrsolv6(double* s, const int* ipvt, const double* diag, const double* qtb, double* x, double* sdiag) {
-  const int n = 6;
+// s: 6x6 (row i, col j at s[j*6+i]); upper triangle = R.  dperm[j] = diag[ipvt[j]].  Every loop has compile-time bounds and is
+// fully unrolled, so s / sdiag / wa live in registers (the rolled form kept them in local memory: an L1 round trip inside
+// every step of the dependent rotation chain).
+__device__ void qrsolv6(double* s, const int* ipvt, const double* dperm, const double* qtb, double* x, double* sdiag) {
+  constexpr int n = 6;
   double wa[6];
+#pragma unroll
   for (int j = 0; j < n; ++j) { x[j] = s[j * 6 + j]; wa[j] = qtb[j]; sdiag[j] = 0; }
-  for (int j = 0; j < n; ++j) for (int i = j + 1; i < n; ++i) s[j * 6 + i] = s[i * 6 + j];
+#pragma unroll
+  for (int j = 0; j < n; ++j)
+#pragma unroll
+    for (int i = j + 1; i < n; ++i) s[j * 6 + i] = s[i * 6 + j];
+  bool live = true;
+#pragma unroll
   for (int j = 0; j < n; ++j) {
-    const int l = ipvt[j];
-    if (diag[l] == 0.) break;
-    for (int k = j; k < n; ++k) sdiag[k] = 0;
-    sdiag[j] = diag[l];
-    double qtbpj = 0.;
-    for (int k = j; k < n; ++k) {
-      double c, sn;
-      givens_d(-s[k * 6 + k], sdiag[k], c, sn);
-      s[k * 6 + k] = c * s[k * 6 + k] + sn * sdiag[k];
-      double temp = c * wa[k] + sn * qtbpj;
-      qtbpj = -sn * wa[k] + c * qtbpj;
-      wa[k] = temp;
-      for (int i = k + 1; i < n; ++i) {
-        temp = c * s[k * 6 + i] + sn * sdiag[i];
-        sdiag[i] = -sn * s[k * 6 + i] + c * sdiag[i];
-        s[k * 6 + i] = temp;
+    if (dperm[j] == 0.) live = false;        // MINPACK: "if (diag[l] == 0) break" out of the elimination loop
+    if (live) {
+#pragma unroll
+      for (int k = j; k < n; ++k) sdiag[k] = 0;
+      sdiag[j] = dperm[j];
+      double qtbpj = 0.;
+#pragma unroll
+      for (int k = j; k < n; ++k) {
+        double c, sn;
+        givens_d(-s[k * 6 + k], sdiag[k], c, sn);
+        s[k * 6 + k] = c * s[k * 6 + k] + sn * sdiag[k];
+        double temp = c * wa[k] + sn * qtbpj;
+        qtbpj = -sn * wa[k] + c * qtbpj;
+        wa[k] = temp;
+#pragma unroll
+        for (int i = k + 1; i < n; ++i) {
+          temp = c * s[k * 6 + i] + sn * sdiag[i];
+          sdiag[i] = -sn * s[k * 6 + i] + c * sdiag[i];
+          s[k * 6 + i] = temp;
+        }
       }
     }
   }
-  int nsing = 0;
-  for (nsing = 0; nsing < n && sdiag[nsing] != 0; nsing++) {}
-  for (int j = nsing; j < n; ++j) wa[j] = 0;
-  for (int i = nsing - 1; i >= 0; --i) {
-    double sum = wa[i];
-    for (int j = i + 1; j < nsing; ++j) sum -= s[i * 6 + j] * wa[j];
-    wa[i] = sum / s[i * 6 + i];
+  int nsing = n;
+#pragma unroll
+  for (int j = n - 1; j >= 0; --j) if (sdiag[j] == 0) nsing = j;      // first zero of sdiag
+#pragma unroll
+  for (int j = 0; j < n; ++j) if (j >= nsing) wa[j] = 0;
+#pragma unroll
+  for (int i = n - 1; i >= 0; --i) {
+    if (i < nsing) {
+      double sum = wa[i];
+#pragma unroll
+      for (int j = i + 1; j < n; ++j) if (j < nsing) sum -= s[i * 6 + j] * wa[j];
+      wa[i] = sum / s[i * 6 + i];
+    }
   }
+#pragma unroll
   for (int j = 0; j < n; ++j) sdiag[j] = s[j * 6 + j];
+#pragma unroll
   for (int j = 0; j < n; ++j) s[j * 6 + j] = x[j];
+#pragma unroll
   for (int j = 0; j < n; ++j) x[ipvt[j]] = wa[j];
 }
 
@@ -250,7 +281,7 @@ __device__ void lmpar6(const double* R, const int* perm, int rank, const double*
     ++iter;
     if (par == 0.) par = fmax(dwarf, .001 * paru);
     const double sp = sqrt(par);
-    for (int j = 0; j < n; ++j) wa1[j] = sp * diag[j];
+    for (int j = 0; j < n; ++j) wa1[j] = sp * diag[perm[j]];      // qrsolv's diag[ipvt[j]], gathered once
     qrsolv6(s, perm, wa1, qtb, x, sdiag);
     for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
     dxnorm = norm6(wa2);
@@ -779,7 +810,8 @@ ESVO_API int esvo_track_solve(esvo_ctx* c, int analytical, double Tout[16], esvo
   a.huber = p.trk_lsnorm == ESVO_TRK_LSNORM_HUBER; a.huber_thr = p.trk_huber_threshold; a.analytical = analytical != 0;
   a.state = t->d.state;
   const int smem = (TRK_MAXB * 6 + TRK_MAXB * 2 + TRK_MAXB * 3 + 16 * 8) * 8;
-  trk_solve_kernel<<<1, TRK_THREADS, smem, c->stream>>>(c->dc, a);
+  static const int trk_threads = [] { const char* e = getenv("ESVO_TRK_THREADS"); int v = e ? atoi(e) : TRK_THREADS; return (v >= 32 && v <= TRK_THREADS && v % 32 == 0) ? v : TRK_THREADS; }();
+  trk_solve_kernel<<<1, trk_threads, smem, c->stream>>>(c->dc, a);
   c->launches += 1;
   ESVO_CUDA_TRY(c, cudaGetLastError());
   double state[64];

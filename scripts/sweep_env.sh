@@ -1,10 +1,14 @@
 #!/bin/bash
-# usage: sweep_env.sh VAR "v1 v2 ..." [repeats] -- runs bench.py (no CPU baseline) once per value of an environment
-# variable (e.g. ESVO_BENCH_SAMPLER "nvml smi"), prints resident / e2e ms per step and host issue statistics
-VAR=$1; VALS=$2; REP=${3:-1}
-for v in $VALS; do for r in $(seq $REP); do
-  env $VAR=$v timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); b=d['breakdown_ms_per_step']; h=d['host_issue_ms']
-print('$VAR=$v', 'resident %.3f ms (%.0fM/s)  e2e %.3f ms (%.0fM/s)  lm %.2f fus %.2f  host res %.3f/%.2f/%.1f e2e %.3f/%.2f/%.1f  clk %s n=%s' % (d['ms_per_step'], d['value']/1e6, d['e2e']['ms_per_step'], d['e2e']['value']/1e6, b['depth_lm'], b['fusion_clean_regularise'], h['resident']['mean'],h['resident']['p99'],h['resident']['max'],h['e2e']['mean'],h['e2e']['p99'],h['e2e']['max'], d['clocks']['sm_mhz'], d['clocks']['samples']))"
-done; done
+# usage: sweep_env.sh "<tag> VAR=val ..." ...   -- one short bench run per argument with the given environment
+for spec in "$@"; do
+  set -- $spec; tag=$1; shift
+  env "$@" python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-parity --no-extras --min-timed-s 0.25 > gpurun_out/b_x.json 2> gpurun_out/b_x.err
+  python - "$tag" <<'PY'
+import json, sys
+try:
+    d = json.loads(open("gpurun_out/b_x.json").read().strip().splitlines()[-1])
+    print("%s: ms/step %.4f e2e %.4f" % (sys.argv[1], d["ms_per_step"], d["e2e"]["ms_per_step"]), {k: round(v, 3) for k, v in d["breakdown_ms_per_step"].items() if k != "source"})
+except Exception as e:
+    print(sys.argv[1], "failed", e, open("gpurun_out/b_x.err").read()[-300:])
+PY
+done
