@@ -11,6 +11,10 @@
 // evaluated in f64 from those integers (mean = S/N is the same single rounding the reference
 // performs; see DESIGN.md "BM cost" for the rounding discussion).  Algorithmic bytes per candidate:
 // 105 px x 4 B = 420 B (SURVEY.md 8d, f32 TS convention).
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace esvo {
@@ -153,6 +157,119 @@ __global__ void __launch_bounds__(BM_WARPS * 32) bm_kernel(DevConsts dc, BmArgs 
 }
 
 // --------------------------------------------------------------------------------------------
+// TMA form (the default since round 2): the right-image strip every candidate window of one event lies in --
+// wy rows x (wx + dmax - dmin) bytes -- is fetched with ONE cp.async.bulk.tensor.2d (tensor map over the pitched u8
+// surface, zero fill outside the image) into shared memory behind an mbarrier; the 32 lanes then read their candidate windows
+// from shared memory instead of issuing per-lane LDG.E.U8 against L1.  Same arithmetic, same results as bm_kernel (horizontal
+// search, step 1 only).  Measured comparison: profiles/r2_tma.md (12.3 M -> 9.1 M instructions, 29 -> 19 us at 346x260).
+// --------------------------------------------------------------------------------------------
+template <int BW>     // box width in bytes (multiple of 16)
+__global__ void __launch_bounds__(32) bm_tma_kernel(DevConsts dc, BmArgs a, const __grid_constant__ CUtensorMap tmap_r) {
+  __shared__ __align__(128) uint8_t s_strip[8 * BW];
+  __shared__ uint8_t s_left[kMaxPatch];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x;
+  if (i >= a.n) return;
+  const int W = dc.W, H = dc.H, wx = dc.wx, wy = dc.wy, N = wx * wy;
+  const int hx = (wx - 1) / 2, hy = (wy - 1) / 2;
+  if (lane == 0) a.out.flag[i] = 0;
+  const int ex = a.ex[i], ey = a.ey[i];
+  if (ex >= W || ey >= H) return;
+  const size_t li = (size_t)ey * W + ex;
+  const double xr0 = a.lut[2 * li], xr1 = a.lut[2 * li + 1];
+  if (xr0 < 0 || xr0 > W - 1 || xr1 < 0 || xr1 > H - 1) return;
+  if (a.mask[(size_t)((int)xr1) * W + (int)xr0] <= 125) return;
+  const int x1x = (int)floor(xr0), x1y = (int)floor(xr1);
+  if (!bm_valid_patch(x1x, x1y, hx, hy, W, H)) return;
+  // issue the strip load first: it flies while the left patch is staged and tested
+  // the inner coordinate of a TMA box must be a multiple of 16 bytes (an unaligned x raises "illegal instruction" on sm_100a,
+  // scripts/tma_test/tma_min.cu): load from the aligned column below and carry the offset
+  const int x_want = x1x - dc.dmax - hx, y_lo = x1y - hy;
+  const int x_lo = x_want & ~15, x_off = x_want - x_lo;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar), dst = (unsigned)__cvta_generic_to_shared(s_strip);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(BW * wy)) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(&tmap_r)), "r"(bar), "r"(x_lo), "r"(y_lo) : "memory");
+  }
+  int Sl = 0, Sll = 0, cnt0 = 0;
+  for (int k = lane; k < N; k += 32) {
+    int py = k / wx, px = k - py * wx;
+    int v = a.tl[(size_t)(x1y - hy + py) * dc.pitch + (x1x - hx + px)];
+    s_left[k] = (uint8_t)v;
+    Sl += v; Sll += v * v; cnt0 += (v < 1);
+  }
+  Sl = warp_sum_i(Sl); Sll = warp_sum_i(Sll); cnt0 = warp_sum_i(cnt0);
+  __syncwarp();
+  {  // every lane waits for the strip (phase 0); the block must not exit while the copy is in flight
+    unsigned done = 0;
+    while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.b32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+  }
+  if ((double)cnt0 > 0.95 * (double)N) return;
+  const int ncand = (dc.dmax >= dc.dmin) ? (dc.dmax - dc.dmin) + 1 : 0;
+  double best = 1.0; int bestDisp = -1; int nev = 0;
+  for (int j = lane; j < ncand; j += 32) {
+    const int disp = dc.dmin + j;
+    const int x2x = x1x - disp;
+    const bool valid = bm_valid_patch(x2x, x1y, hx, hy, W, H);
+    double c = 1.0;
+    if (valid) {
+      const uint8_t* base = s_strip + x_off + (dc.dmax - disp);
+      int Sr = 0, Srr = 0, Slr = 0;
+      for (int py = 0; py < wy; ++py) {
+        const uint8_t* row = base + py * BW;
+        const uint8_t* lrow = &s_left[py * wx];
+#pragma unroll 5
+        for (int px = 0; px < wx; ++px) { int r = row[px], l = lrow[px]; Sr += r; Srr += r * r; Slr += l * r; }
+      }
+      c = bm_cost_from_moments(N, Sl, Sll, Sr, Srr, Slr);
+    }
+    nev += valid;
+    if (valid && c <= best) { best = c; bestDisp = disp; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ob = __shfl_xor_sync(0xffffffffu, best, o); int od = __shfl_xor_sync(0xffffffffu, bestDisp, o);
+    if (od >= 0 && (bestDisp < 0 || ob < best || (ob == best && od > bestDisp))) { best = ob; bestDisp = od; }
+  }
+  nev = warp_sum_i(nev);
+  const bool coarse_ok = bestDisp >= 0 && best < dc.zncc_thr;
+  if (!coarse_ok) { if (lane == 0) atomicAdd(&a.counters[5], (unsigned long long)nev); return; }
+  // fine search of step 1 re-evaluates the best candidate once (EventBM.cpp:126-136): same cost, one more evaluation
+  if (lane == 0) atomicAdd(&a.counters[5], (unsigned long long)(nev + 1));
+  if (!(best < dc.zncc_thr)) return;
+  if (lane == 0) {
+    const double te = ns_to_sec_dev(a.et[i]);
+    int lo = 0, hi = a.n_poses;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (ns_to_sec_dev(a.pose_t[mid]) < te) lo = mid + 1; else hi = mid; }
+    if (lo == a.n_poses) return;
+    a.out.disp[i] = bestDisp; a.out.pose_idx[i] = lo; a.out.cost[i] = best;
+    a.out.xrect[2 * i] = xr0; a.out.xrect[2 * i + 1] = xr1;
+    a.out.flag[i] = 1;
+  }
+}
+
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_u8_tensor_map(CUtensorMap* tm, const uint8_t* img, int W, int H, int pitch, int boxw, int boxh) {
+  static tmap_encode_fn enc = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) fn = nullptr;
+    return (tmap_encode_fn)fn;
+  }();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)W, (cuuint64_t)H};
+  const cuuint64_t gstr[1] = {(cuuint64_t)pitch};
+  const cuuint32_t box[2] = {(cuuint32_t)boxw, (cuuint32_t)boxh}, estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)img, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// --------------------------------------------------------------------------------------------
 // Ordered compaction.  The reference fans events out to NT threads with the interleave
 // i = tid, tid+NT, ... and concatenates the per-thread result vectors (EventBM.cpp:295-315,
 // DepthProblemSolver.cpp:65-90), so position(i) = #accepted in classes < i%NT + #accepted
@@ -244,6 +361,21 @@ int bm_run(Ctx* c) {
   a.ex = c->d_ex; a.ey = c->d_ey; a.et = c->d_et; a.n = (int)c->n_ev; a.lut = c->d_lut; a.mask = c->d_mask;
   a.tl = c->obs_ls; a.tr = c->obs_rs; a.pose_t = c->d_pose_t; a.n_poses = (int)c->n_poses; a.out = c->bm;
   a.counters = (unsigned long long*)c->d_counters;
+  // TMA-staged strips by default (19 vs 29 us at 346x260, 96 vs 142 us at 640x480, identical results: profiles/r2_tma.md);
+  // ESVO_BM_TMA=0 selects the per-lane LDG kernel, which also serves step > 1, the up-down rig and very wide searches
+  static const int use_tma = getenv("ESVO_BM_TMA") ? atoi(getenv("ESVO_BM_TMA")) : 1;
+  const int strip = c->dc.wx + c->dc.dmax - c->dc.dmin + 15;     // + alignment slack of the box origin
+  if (use_tma && c->dc.step == 1 && !c->dc.updown && c->dc.wy <= 8 && strip <= 112 && c->dc.dmax >= c->dc.dmin) {
+    CUtensorMap tm;
+    const int bw = strip <= 64 ? 64 : 112;
+    if (make_u8_tensor_map(&tm, c->obs_rs, c->dc.W, c->dc.H, c->dc.pitch, bw, c->dc.wy)) {
+      if (bw == 64) bm_tma_kernel<64><<<(int)c->n_ev, 32, 0, c->stream>>>(c->dc, a, tm);
+      else bm_tma_kernel<112><<<(int)c->n_ev, 32, 0, c->stream>>>(c->dc, a, tm);
+      c->launches += 1;
+      ESVO_CUDA_TRY(c, cudaGetLastError());
+      return ESVO_OK;
+    }
+  }
   bm_kernel<<<div_up((int)c->n_ev, BM_WARPS), BM_WARPS * 32, 0, c->stream>>>(c->dc, a);
   c->launches += 1;
   ESVO_CUDA_TRY(c, cudaGetLastError());
