@@ -588,7 +588,7 @@ def run_ours(args, rank, world, local_rank):
     # Weak scaling needs the same work on every GPU: the headline replays the SAME synthetic stream shape on every rank (scene
     # seed 10; time origin differs per rank).  `--streams distinct` gives every rank its own scene (seeds 10, 11, ... as in
     # SURVEY cfg 5); under N > 1 a short distinct-scenes pass is ALSO run and reported as extras.distinct_streams.
-    base = make_workload(seed=edist.stream_seed(rank if args.streams == "distinct" else 0))
+    base = make_workload(seed=edist.stream_seed(rank if args.streams == "distinct" else 0, base=args.scene_seed))
     if args.streams != "distinct" and rank:
         base = shifted(base, 100000 * rank)
     K, Wm = args.steps, args.warmup
@@ -609,7 +609,16 @@ def run_ours(args, rank, world, local_rank):
     _, e2e_evals_all, _ = edist.reduce_and_gather(med_e, float(e2e_evals), rec, device="cuda")
     per_rank = edist.gather_scalars([float(np.median(m["region_ms"])) / K, float(np.median(m["e2e_region_ms"])) / K,
                                      float(np.mean(m["issue_resident_ms"])), float(np.mean(m["issue_e2e_ms"]))], device="cuda")
+    # isolated launches + FP64 probe on rank 0 while this ctx is still alive, then the ctx is closed: a second live ctx would push
+    # the process past CUDA_DEVICE_MAX_CONNECTIONS hardware queues and serialise the pipeline streams of the next one
     extras = {}
+    iso = tfl_value = None
+    if rank == 0:
+        iso = isolated_kernels(g, base)
+        tfl = C.c_double(0)
+        g._call("debug_fp64_probe", [C.POINTER(C.c_double)], C.byref(tfl))
+        tfl_value = float(tfl.value)
+    g.close()
     if world > 1 and args.streams != "distinct" and not args.no_extras:
         # SURVEY cfg 5 flavour: every GPU its own scene (distinct maps), a short pass on a fresh ctx
         g2 = capi.Backend(prod, l, r, prm, device=local_rank)
@@ -623,6 +632,27 @@ def run_ours(args, rank, world, local_rank):
                                       "note": "every GPU its own scene (seeds 10..): per-frame work differs between GPUs, the step time is the slowest stream's",
                                       "streams": [dict(zip(edist.RECORD_FIELDS, [float(v) for v in q])) for q in recs2]}
         g2.close()
+        # BASELINE configs[4]: eight independent 640x480 (DSEC-shaped) streams, one per GPU (here: one per rank that exists)
+        try:
+            cfg5 = CONFIGS["cfg3"]
+            l5, r5 = configs.rig_calibs(cfg5["rig"])
+            prm5 = configs.params_for(cfg5["rig"], prod)
+            g5 = capi.Backend(prod, l5, r5, prm5, device=local_rank)
+            g5._call("set_pipeline_depth", [C.c_int], args.pipeline_depth)
+            base5 = make_workload(seed=edist.stream_seed(rank), cfg="cfg3")
+            K5 = min(K, 10)
+            m5 = measure_stream(args, g5, base5, world, local_rank, ClockSampler(local_rank), K5, 3, prm5, want_breakdown=False, target_s=0.05, max_regions=6)
+            reg5 = edist.gather_scalars(m5["region_ms"], device="cuda").max(axis=0)
+            reg5e = edist.gather_scalars(m5["e2e_region_ms"], device="cuda").max(axis=0)
+            rec5 = edist.make_record(edist.stream_seed(rank), K5, m5["e2e_ctr"], edist.map_checksum(g5.map_download()))
+            _, ev5, recs5 = edist.reduce_and_gather(0.0, float(m5["ctr"]["bm_evals"] + m5["lm_exec"]), rec5, device="cuda")
+            extras["cfg5_dsec_streams"] = {"workload": f"BASELINE configs[4]: {world} independent 640x480 (DSEC-shaped) stereo event streams, one per GPU (scene seeds 10..)",
+                                           "value": ev5 * K5 / (float(np.median(reg5)) * 1e-3), "unit": "evals/s", "ms_per_step": float(np.median(reg5)) / K5,
+                                           "e2e_ms_per_step": float(np.median(reg5e)) / K5, "steps_per_region": K5, "regions": int(len(reg5)),
+                                           "streams": [dict(zip(edist.RECORD_FIELDS, [float(v) for v in q])) for q in recs5]}
+            g5.close()
+        except Exception as ex:
+            extras["cfg5_dsec_streams"] = {"error": repr(ex)}
     if rank != 0:
         return
     clocks = sampler.stop()
@@ -665,9 +695,6 @@ def run_ours(args, rank, world, local_rank):
         "streams": [dict(zip(edist.RECORD_FIELDS, [float(v) for v in q])) for q in records],
     }
     # ---------------- roofline of the dominant kernel: isolated launch, measured FP64 peak ----------------
-    iso = isolated_kernels(g, base)
-    tfl = C.c_double(0)
-    g._call("debug_fp64_probe", [C.POINTER(C.c_double)], C.byref(tfl))
     ncu = load_ncu_counters()
     lm_ms, bm_ms = iso["lm_ms"], iso["bm_ms"]
     ncand = iso["bm_evals"] / max(iso["n_events"], 1)
@@ -680,8 +707,8 @@ def run_ours(args, rank, world, local_rank):
         "why": "dependent FP64 issue: the time-surface pair is L1/L2-resident (DRAM traffic ~1.5 % of the algorithmic bytes); ncu shows the FP64 pipe "
                "and the issue slots as the busiest units (profiles/r2_*), so the roofline is the FP64 rate.  The HBM view the north star asked "
                "for is kept under `hbm`.",
-        "achieved": (lm_flops / (lm_ms * 1e-3) / 1e12) if lm_flops else None, "peak": float(tfl.value), "unit": "TFLOP/s",
-        "frac": (lm_flops / (lm_ms * 1e-3) / 1e12 / tfl.value) if lm_flops else None,
+        "achieved": (lm_flops / (lm_ms * 1e-3) / 1e12) if lm_flops else None, "peak": tfl_value, "unit": "TFLOP/s",
+        "frac": (lm_flops / (lm_ms * 1e-3) / 1e12 / tfl_value) if lm_flops else None,
         "peak_kind": "measured in this run (esvo_debug_fp64_probe: dependent DFMA chains, 2 flops per FMA)",
         "ms_per_launch": lm_ms, "launch": "one isolated launch on an idle GPU (esvo_depth_solve on the frame's seeds), CUDA events inside the library",
         "evals_per_launch": iso["lm_exec"], "seeds_per_launch": iso["n_seeds"], "fp64_flops_per_eval": flops_per_eval,
@@ -694,7 +721,6 @@ def run_ours(args, rank, world, local_rank):
     out["roofline_other"] = {"kernel": "bm_kernel", "bound": "hbm", "achieved": bm_bytes / (bm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": bm_bytes / (bm_ms * 1e-3) / 1e9 / peak, "peak_kind": peak_kind, "ms_per_launch": bm_ms,
                              "algorithmic_bytes_per_launch": bm_bytes, "traffic": (ncu or {}).get("bm_dram_bytes_per_launch")}
-    g.close()
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_leg(base, sample_steps=3)
         ws = cpu_leg(base, sample_steps=3, shortcut=True)
@@ -830,6 +856,7 @@ def main():
     ap.add_argument("--parity-frames", type=int, default=3)
     ap.add_argument("--min-timed-s", type=float, default=0.5, help="repeat the K-step region until this much time has been timed")
     ap.add_argument("--streams", default="same", choices=["same", "distinct"], help="per-GPU synthetic streams: same shape (equal work) or distinct scenes")
+    ap.add_argument("--scene-seed", type=int, default=10, help="seed of the synthetic scene (rank r uses seed + r with --streams distinct)")
     ap.add_argument("--pipeline-depth", type=int, default=16, help="frames in flight per stream (1 = strictly sequential)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(32) bm_tma_kernel(DevConsts dc, BmArgs a, cons
 
 typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static bool make_u8_tensor_map(CUtensorMap* tm, const uint8_t* img, int W, int H, int pitch, int boxw, int boxh) {
+bool make_u8_tensor_map(CUtensorMap* tm, const uint8_t* img, int W, int H, int pitch, int boxw, int boxh) {
   static tmap_encode_fn enc = [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qr;

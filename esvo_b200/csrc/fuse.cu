@@ -42,6 +42,7 @@ struct MapState {
   size_t prop_cap = 0, staged = 0;
   int32_t* head = nullptr;       // per pixel, -1 = empty
   int32_t* next = nullptr;       // per contribution (9 per staged point)
+  int32_t* sort_pool = nullptr;  // ids of the long contribution lists, one segment per pixel (capacity = all contributions)
   int32_t* active = nullptr;     // pixels touched since the last reset, in first-touch order (count in d_scal[3])
   uint32_t* cbits = nullptr;     // one bit per contribution id: "this contribution created its pixel's element" (ordered hand-off)
   uint32_t* cprefix = nullptr;   // exclusive popcount prefix per word of cbits
@@ -54,7 +55,7 @@ struct MapState {
   double T_frame_world[16];
   esvo_depth_point* d_dl = nullptr;      // download staging
   unsigned long long* d_dl_keys = nullptr;
-  unsigned long long* d_scal = nullptr;  // [0] n_fusions, [1] download count, [2] map size, [3] number of active pixels
+  unsigned long long* d_scal = nullptr;  // [0] n_fusions, [1] download count, [2] map size, [3] number of active pixels, [5] sort-pool cursor
   unsigned long long* h_scal = nullptr;
 };
 
@@ -264,10 +265,25 @@ __device__ __forceinline__ void fold_store(const DevConsts& dc, MapSoA& M, int p
 }
 
 // Thread-per-active-pixel form (dense over the active list): the production form (see fuse_finish for the measurement).
+__device__ __forceinline__ void heap_sort_i32(int* ids, int cnt) {
+  auto sift = [&](int start, int end) {
+    int root = start;
+    while (2 * root + 1 <= end) {
+      int child = 2 * root + 1, sw = root;
+      if (ids[sw] < ids[child]) sw = child;
+      if (child + 1 <= end && ids[sw] < ids[child + 1]) sw = child + 1;
+      if (sw == root) return;
+      int tmp = ids[root]; ids[root] = ids[sw]; ids[sw] = tmp;
+      root = sw;
+    }
+  };
+  for (int st = (cnt - 2) / 2; st >= 0; --st) sift(st, cnt - 1);
+  for (int end = cnt - 1; end > 0; --end) { int tmp = ids[end]; ids[end] = ids[0]; ids[0] = tmp; sift(0, end - 1); }
+}
 template <bool NAIVE>
 __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* head, const int32_t* __restrict__ next,
                                  const int32_t* __restrict__ active, unsigned long long seq_base, unsigned long long* scal,
-                                 uint32_t* cbits, CleanArgs clean) {
+                                 uint32_t* cbits, CleanArgs clean, int32_t* sort_pool) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if ((unsigned long long)t >= scal[3]) return;
   const int pix = active[t];
@@ -285,21 +301,7 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
   if (total <= CAP) {
     if (cnt <= 16) {
       for (int a = 1; a < cnt; ++a) { int v = ids[a], b = a - 1; while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; } ids[b + 1] = v; }
-    } else {  // heap sort, O(L log L) on the local array
-      auto sift = [&](int start, int end) {
-        int root = start;
-        while (2 * root + 1 <= end) {
-          int child = 2 * root + 1, sw = root;
-          if (ids[sw] < ids[child]) sw = child;
-          if (child + 1 <= end && ids[sw] < ids[child + 1]) sw = child + 1;
-          if (sw == root) return;
-          int tmp = ids[root]; ids[root] = ids[sw]; ids[sw] = tmp;
-          root = sw;
-        }
-      };
-      for (int st = (cnt - 2) / 2; st >= 0; --st) sift(st, cnt - 1);
-      for (int end = cnt - 1; end > 0; --end) { int tmp = ids[end]; ids[end] = ids[0]; ids[0] = tmp; sift(0, end - 1); }
-    }
+    } else heap_sort_i32(ids, cnt);   // O(L log L) on the local array
     FoldRec cur = P.hot[ids[0] / 9];
     for (int a = 0; a < cnt; ++a) {              // the next record is in flight while this one is folded
       FoldRec nxt = cur;
@@ -307,13 +309,19 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
       fold_apply<NAIVE>(dc, P, f, row, col, ids[a], cur, seq_base);
       cur = nxt;
     }
-  } else {  // long list: repeated minimum selection, O(L^2) walks, no storage
-    int last = -1;
+  } else {
+    // long list (dense scenes: several hundred contributions on one pixel): its ids go to a private segment of the sort pool
+    // (the pool holds one int per contribution, so the segments of all pixels always fit), heap-sorted there, replayed as above
+    int* seg = sort_pool + atomicAdd(&scal[5], (unsigned long long)total);
+    int k = 0;
+    for (int q = h; q >= 0; q = next[q]) seg[k++] = q;
+    heap_sort_i32(seg, total);
+    FoldRec cur = P.hot[seg[0] / 9];
     for (int a = 0; a < total; ++a) {
-      int best = 0x7fffffff;
-      for (int q = h; q >= 0; q = next[q]) if (q > last && q < best) best = q;
-      fold_apply<NAIVE>(dc, P, f, row, col, best, P.hot[best / 9], seq_base);
-      last = best;
+      FoldRec nxt = cur;
+      if (a + 1 < total) nxt = P.hot[seg[a + 1] / 9];
+      fold_apply<NAIVE>(dc, P, f, row, col, seg[a], cur, seq_base);
+      cur = nxt;
     }
   }
   fold_store(dc, M, pix, f, clean, cbits, seq_base, scal);
@@ -798,13 +806,13 @@ static int prop_reserve(Ctx* c, size_t need) {
   size_t cap = std::max<size_t>(need, 65536);
   PropSoA& P = ms->p;
   void* olds[] = {P.hot, P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col, ms->next,
-                  ms->cbits, ms->cprefix};
+                  ms->cbits, ms->cprefix, ms->sort_pool};
   for (void* p : olds) if (p) cudaFree(p);
   ESVO_CUDA_TRY(c, dm(&P.ok, cap)); ESVO_CUDA_TRY(c, dm(&P.hot, cap));
   double** ds[] = {&P.rho, &P.s2, &P.nu, &P.var, &P.res, &P.x0, &P.x1, &P.pc0, &P.pc1, &P.pc2};
   for (double** d : ds) ESVO_CUDA_TRY(c, dm(d, cap));
   ESVO_CUDA_TRY(c, dm(&P.age, cap)); ESVO_CUDA_TRY(c, dm(&P.row, cap)); ESVO_CUDA_TRY(c, dm(&P.col, cap));
-  ESVO_CUDA_TRY(c, dm(&ms->next, cap * 9));
+  ESVO_CUDA_TRY(c, dm(&ms->next, cap * 9)); ESVO_CUDA_TRY(c, dm(&ms->sort_pool, cap * 9));
   ms->cbits_words = (cap * 9 + 31) / 32;
   ESVO_CUDA_TRY(c, dm(&ms->cbits, ms->cbits_words)); ESVO_CUDA_TRY(c, dm(&ms->cprefix, ms->cbits_words));
   ms->prop_cap = cap;
@@ -825,11 +833,11 @@ int fuse_alloc(Ctx* c) {
   ESVO_CUDA_TRY(c, dm(&ms->head, npix));
   ESVO_CUDA_TRY(c, dm(&ms->active, npix));
   ESVO_CUDA_TRY(c, dm(&ms->d_dl, npix)); ESVO_CUDA_TRY(c, dm(&ms->d_dl_keys, npix));
-  ESVO_CUDA_TRY(c, dm(&ms->d_scal, 4));
+  ESVO_CUDA_TRY(c, dm(&ms->d_scal, 8));
   ESVO_CUDA_TRY(c, cudaMallocHost((void**)&ms->h_scal, 4 * 8));
   ESVO_CUDA_TRY(c, cudaMemset(M.exists, 0, npix));
   ESVO_CUDA_TRY(c, cudaMemset(ms->head, 0xff, npix * 4));   // invariant: every fold leaves the heads it consumed at -1
-  ESVO_CUDA_TRY(c, cudaMemset(ms->d_scal, 0, 4 * 8));
+  ESVO_CUDA_TRY(c, cudaMemset(ms->d_scal, 0, 8 * 8));
   for (int i = 0; i < 16; ++i) ms->T_world_frame[i] = ms->T_frame_world[i] = (i % 5 == 0) ? 1.0 : 0.0;
   ms->list_valid = true; ms->folds = 0;
   return prop_reserve(c, 65536);
@@ -840,7 +848,7 @@ void fuse_free(Ctx* c) {
   MapSoA& M = ms->m; PropSoA& P = ms->p;
   void* ps[] = {M.exists, M.rho, M.s2, M.nu, M.var, M.res, M.x0, M.x1, M.pc0, M.pc1, M.pc2, M.rho_tmp, M.age, M.row, M.col,
                 M.first_key, P.hot, P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col,
-                ms->head, ms->next, ms->active, ms->cbits, ms->cprefix, ms->d_dl, ms->d_dl_keys, ms->d_scal};
+                ms->head, ms->next, ms->active, ms->cbits, ms->cprefix, ms->sort_pool, ms->d_dl, ms->d_dl_keys, ms->d_scal};
   for (void* p : ps) if (p) cudaFree(p);
   if (ms->h_scal) cudaFreeHost(ms->h_scal);
   delete ms;
@@ -853,7 +861,7 @@ int fuse_reset_map(Ctx* c, const double T[16]) {
   MapState* ms = c->map;
   const size_t npix = (size_t)c->dc.W * c->dc.H;
   ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->m.exists, 0, npix, c->stream));
-  ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->d_scal, 0, 32, c->stream));
+  ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->d_scal, 0, 64, c->stream));
   std::memcpy(ms->T_world_frame, T, 128);
   // rigid inverse (kindr Transformation::inverse)
   double* I = ms->T_frame_world;
@@ -871,7 +879,7 @@ int fuse_reset_map(Ctx* c, const double T[16]) {
 static int fuse_begin_round(Ctx* c) {
   MapState* ms = c->map;
   if (ms->staged == 0 && ms->folds > 0) {
-    ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->d_scal + 3, 0, 8, c->stream));
+    ESVO_CUDA_TRY(c, cudaMemsetAsync(ms->d_scal + 3, 0, 24, c->stream));   // active count, (spare), sort-pool cursor
     ms->list_valid = false;
   }
   return ESVO_OK;
@@ -952,8 +960,8 @@ int fuse_finish(Ctx* c, bool naive, const double* clean4) {
   if (!warp_fold) {
     const int npix = c->dc.W * c->dc.H, B = 32;
     const int bound = (int)std::min<size_t>((size_t)npix, ms->staged * 9);
-    if (naive) fuse_fold_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
-    else fuse_fold_kernel<false><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+    if (naive) fuse_fold_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool);
+    else fuse_fold_kernel<false><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool);
   } else {   // persistent: one-warp blocks walk the active list, one warp per pixel
     static const int G = getenv("ESVO_DBG_FOLD_GRID") ? atoi(getenv("ESVO_DBG_FOLD_GRID")) : 148 * 16;
     static const int wpb = getenv("ESVO_DBG_FOLD_WPB") ? atoi(getenv("ESVO_DBG_FOLD_WPB")) : 1;

@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from esvo_b200 import capi, configs, synth
 prod = capi.load_product()
-s = synth.make_stream("hkust", seed=10, n_seeds=5000, history_ms=50.0)
+s = synth.make_stream("hkust", seed=int(os.environ.get("PROBE_SEED", "10")), n_seeds=5000, history_ms=50.0)
 l, r = configs.rig_calibs("hkust")
 g = capi.Backend(prod, l, r, configs.params_for("hkust", prod))
 for cam, side in ((0, "left"), (1, "right")):

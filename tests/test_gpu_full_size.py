@@ -59,6 +59,16 @@ def test_cfg2_benchmarked_configuration_matches_oracle(product_lib):
         assert t["stats_equal"] and t["pose_max_abs_diff_vs_oracle"] < 1e-6 and t["translation_rel_diff_vs_oracle"] < 1e-4, t
 
 
+def test_dense_scene_long_contribution_lists_match_oracle(product_lib):
+    """Scene 11 of the synthetic generator is denser (85 k events per frame): single pixels collect several hundred
+    contributions over the 20-frame window, which takes the fold's sort-pool path (lists longer than its local array)."""
+    import bench
+    base = bench.make_workload(seed=11)
+    par, _ = bench.parity_block(product_lib, base, "hkust", n_check=2, tracking=False)
+    print("scene 11 parity:", par)
+    _assert_parity(par)
+
+
 def test_cfg3_dsec_benchmarked_configuration_matches_oracle(product_lib):
     """SURVEY 8d cfg 3: 640x480 dsec rig, 20 000 events, disparity [0, 80], fusion_radius 1, SmoothTimeSurface, 5-frame window
     (mapping_dsec.yaml): window primed with 5 frames, 2 more compared."""
