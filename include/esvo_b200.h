@@ -271,6 +271,43 @@ ESVO_API int esvo_window_download(esvo_ctx* ctx, int index, esvo_depth_point* ou
 /* Drops the fusion window (dqvDepthPoints_) -- the reference does this on reset. */
 ESVO_API int esvo_mapping_reset(esvo_ctx* ctx);
 
+/* ---------------- comparison modes of esvo_MVStereo ---------------- */
+/* EventMatcher parameters: EventMatcher ctor / resetParameters (esvo_core/src/core/EventMatcher.cpp:9-49) as esvo_MVStereo
+ * fills them from its yaml (esvo_core/src/esvo_MVStereo.cpp:81-91: EM_Time_THRESHOLD, EM_EPIPOLAR_THRESHOLD,
+ * EM_TS_NCC_THRESHOLD, patch_size_X/Y) and its thread count NUM_THREAD_MAPPING (:45; output order only). */
+typedef struct {
+  double time_threshold_s;   /* EM_Time_THRESHOLD   (5e-5; 5e-4 in the shipped yamls) */
+  double epipolar_threshold; /* EM_EPIPOLAR_THRESHOLD (0.5; 1.0)                       */
+  double ts_ncc_threshold;   /* EM_TS_NCC_THRESHOLD (0.1)                              */
+  int32_t patch_size_x, patch_size_y;
+  int32_t num_thread;
+  int32_t _pad;
+} esvo_em_params;
+
+/* replaces: EventMatcher::createMatchProblem + match_all_HyperThread / match / match_an_event
+ * (esvo_core/src/core/EventMatcher.cpp:51-58,60-163,185-251) -- the event-to-event matcher of [26] the reference keeps for
+ * its MVStereo modes 0 and 2: per left event the time-ordered right events within +-time_threshold/2 of the same polarity
+ * (temporal check), within epipolar_threshold rows of the rectified left event and left of it (epipolar check) are
+ * triangulated and scored by the ZNCC of the two time-surface patches warped with that depth (warping2,
+ * patchInterpolation2, zncc_cost :253-346); the cheapest one below ts_ncc_threshold wins.
+ * Left events: the contiguous events of all slices (eventSlicingForEM, esvo_MVStereo.cpp:1008-1040); slice_counts[s] =
+ * EventSlice::numEvents_, slice_poses[16 s] = EventSlice::transf_ (T_world_virtual, row-major).  Right events: the
+ * candidate vector vEventsPtr_right_, time-ordered.  Uses the observation pair of esvo_set_ts_pair.
+ * seeds_out in the reference's thread-major order; *n_seeds: in = capacity, out = count; n_patch_evals = zncc_cost calls. */
+ESVO_API int esvo_em_match(esvo_ctx* ctx, const esvo_em_params* prm, const uint16_t* lx, const uint16_t* ly,
+                           const int64_t* lt_ns, const uint8_t* lpol, size_t n_left, const int32_t* slice_counts,
+                           const double* slice_poses, size_t n_slices, const uint16_t* rx, const uint16_t* ry,
+                           const int64_t* rt_ns, const uint8_t* rpol, size_t n_right, esvo_seed* seeds_out,
+                           size_t* n_seeds, uint64_t* n_patch_evals);
+/* replaces: esvo_MVStereo::vEMP2vDP (esvo_core/src/esvo_MVStereo.cpp:1072-1097): EventMatchPairs -> Gaussian DepthPoints
+ * (row/col = floor of the rectified coordinate, variance bounded to 1e-6, residual = cost, age = age_vis_threshold). */
+ESVO_API int esvo_seeds_to_points(esvo_ctx* ctx, const esvo_seed* seeds, size_t n, esvo_depth_point* pts_out);
+/* replaces: DepthFusion::naive_propagation (esvo_core/src/core/DepthFusion.cpp:232-327) of one DepthPoint vector into the
+ * ctx's DepthFrame (nearest wins, no fusion) -- the accumulation step of MVStereo modes 0, 1 and 4
+ * (esvo_MVStereo.cpp:280-286,355-361,423-427).  reset_map as in esvo_fuse. */
+ESVO_API int esvo_naive_propagate(esvo_ctx* ctx, const esvo_depth_point* pts, size_t n, const double T_world_frame[16],
+                                  int reset_map);
+
 /* ---------------- tracking ---------------- */
 /* replaces: RegProblemSolverLM::resetRegProblem -> RegProblemLM::setProblem
  * (RegProblemSolverLM.cpp:45-74, RegProblemLM.cpp:24-68).  ref_xyz: the reference point cloud in

@@ -12,6 +12,7 @@
 #include <thread>
 
 #include "o_tracking.h"
+#include "o_event_matcher.h"
 
 using namespace oracle;
 
@@ -200,6 +201,46 @@ OAPI int esvo_oracle_init_from_disparity(esvo_oracle_ctx* c, const int16_t* disp
   c->window.push_back(vdp);                                                        // :485
   c->fusor.naive_propagation(vdp, c->dmap, c->T_world_frame);                      // :486
   if (accepted) *accepted = 1;
+  return ESVO_OK;
+}
+// ---- comparison modes of esvo_MVStereo ----
+// EventMatcher::createMatchProblem + match_all_HyperThread (EventMatcher.cpp:51-58,185-251) on the current observation pair
+OAPI int esvo_oracle_em_match(esvo_oracle_ctx* c, const esvo_em_params* prm, const uint16_t* lx, const uint16_t* ly, const int64_t* lt,
+                              const uint8_t* lp, size_t nl, const int32_t* slice_counts, const double* slice_poses, size_t n_slices,
+                              const uint16_t* rx, const uint16_t* ry, const int64_t* rt, const uint8_t* rp, size_t nr, esvo_seed* out,
+                              size_t* n_seeds, uint64_t* n_evals) {
+  if (!c || !prm || !n_seeds || (nl && (!lx || !ly || !lt || !lp)) || (nr && (!rx || !ry || !rt || !rp)) || (n_slices && (!slice_counts || !slice_poses)))
+    return ESVO_ERR_INVALID_ARG;
+  if (c->obs.empty) return ESVO_ERR_STATE;
+  EventMatcher em;
+  em.cs = &c->cs; em.obs = &c->obs; em.NT = prm->num_thread < 1 ? 1 : prm->num_thread;
+  em.time_thr = prm->time_threshold_s; em.epi_thr = prm->epipolar_threshold; em.ncc_thr = prm->ts_ncc_threshold;
+  em.wx = prm->patch_size_x; em.wy = prm->patch_size_y;
+  std::vector<Seed> v;
+  em.match_all(lx, ly, lt, lp, nl, slice_counts, slice_poses, n_slices, rx, ry, rt, rp, nr, v);
+  if (n_evals) *n_evals = em.n_evals;
+  if (v.size() > *n_seeds) { *n_seeds = v.size(); return ESVO_ERR_CAPACITY; }
+  for (size_t i = 0; i < v.size(); ++i) seed_to_pod(v[i], out + i);
+  *n_seeds = v.size();
+  return ESVO_OK;
+}
+// esvo_MVStereo::vEMP2vDP (esvo_MVStereo.cpp:1072-1097)
+OAPI int esvo_oracle_seeds_to_points(esvo_oracle_ctx* c, const esvo_seed* seeds, size_t n, esvo_depth_point* out) {
+  if (!c || (n && (!seeds || !out))) return ESVO_ERR_INVALID_ARG;
+  std::vector<Seed> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = seed_from_pod(seeds[i]);
+  std::vector<DepthPoint> vdp;
+  vEMP2vDP(c->cs, v, (double)c->prm.age_vis_threshold, vdp);
+  for (size_t i = 0; i < n; ++i) to_pod(vdp[i], out + i);
+  return ESVO_OK;
+}
+// DepthFusion::naive_propagation (DepthFusion.cpp:232-288) of one vector into the ctx's DepthFrame
+OAPI int esvo_oracle_naive_propagate(esvo_oracle_ctx* c, const esvo_depth_point* pts, size_t n, const double T[16], int reset_map) {
+  if (!c || (n && !pts)) return ESVO_ERR_INVALID_ARG;
+  if (reset_map) { if (!T) return ESVO_ERR_INVALID_ARG; c->dmap.reset(c->cs.left.W, c->cs.left.H); c->T_world_frame = Mat4::from(T); }
+  std::vector<DepthPoint> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = from_pod(pts[i]);
+  c->fusor.naive_propagation(v, c->dmap, c->T_world_frame);
   return ESVO_OK;
 }
 OAPI int esvo_oracle_ts_set_unordered_input(esvo_oracle_ctx*, int, int) { return ESVO_OK; }   // the literal port always handles it

@@ -25,6 +25,12 @@ for d in lines:
         md += ["", f"## roofline ({d['n_gpus']} GPU)", "", "```", json.dumps(r, indent=1), "```",
                "", "breakdown (separate profiled pass, stages of different slots overlap):", "", "```", json.dumps(d.get("breakdown_ms_per_step"), indent=1), "```",
                "", "host issue per step (ms):", "", "```", json.dumps(d.get("host_issue_ms"), indent=1), "```"]
+    if "parity" in d:
+        md += ["", f"## parity block of the run ({d['n_gpus']} GPU): product vs oracle on the benchmarked configuration", "", "```", json.dumps(d["parity"], indent=1), "```"]
+    for k, v in (d.get("extras") or {}).items():
+        md += ["", f"## extras.{k}", "", "```", json.dumps(v, indent=1), "```"]
+    if "timing" in d:
+        md += ["", "timing:", "", "```", json.dumps(d["timing"], indent=1), "```"]
     if "cpu_baseline" in d and d.get("impl") != "reference":
         md += ["", "cpu_baseline:", "", "```", json.dumps(d["cpu_baseline"], indent=1), "```"]
 open(os.path.join(out, f"{tag}_bench.md"), "w").write("\n".join(md) + "\n")
