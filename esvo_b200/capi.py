@@ -60,6 +60,12 @@ class Params(C.Structure):
     ]
 
 
+class EmParams(C.Structure):
+    """esvo_em_params (include/esvo_b200.h): EventMatcher thresholds / patch size / thread count."""
+    _fields_ = [("time_threshold_s", C.c_double), ("epipolar_threshold", C.c_double), ("ts_ncc_threshold", C.c_double),
+                ("patch_size_x", C.c_int32), ("patch_size_y", C.c_int32), ("num_thread", C.c_int32), ("_pad", C.c_int32)]
+
+
 class LMStats(C.Structure):
     _fields_ = [("n_points", C.c_int64), ("nfev", C.c_int64), ("n_iter", C.c_int64)]
 
@@ -288,6 +294,39 @@ class Backend:
         self._call("fuse", [C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_int)],
                    pts.ctypes.data_as(C.c_void_p), pts.size, _ptr(T, C.c_double), fusion_radius, int(reset_map), C.byref(nf))
         return nf.value
+
+    # ---- comparison modes of esvo_MVStereo (EventMatcher.cpp, esvo_MVStereo.cpp:257-431,1072-1097) ----
+    def em_match(self, left, right, slice_counts, slice_poses, time_thr=5e-4, epi_thr=1.0, ncc_thr=0.1, patch=(15, 7), num_thread=4):
+        """left / right: dicts with x, y, t (ns), p arrays (right time-ordered); slices over the left events."""
+        prm = EmParams(time_thr, epi_thr, ncc_thr, patch[0], patch[1], num_thread, 0)
+
+        def ev(d):
+            return (_arr(d["x"], np.uint16), _arr(d["y"], np.uint16), _arr(d["t"], np.int64), _arr(d["p"], np.uint8))
+        lx, ly, lt, lp = ev(left); rx, ry, rt, rp = ev(right)
+        sc = _arr(slice_counts, np.int32); sp = _arr(slice_poses, np.float64)
+        out = np.zeros(max(lx.size, 1), SEED_DTYPE)
+        n = C.c_size_t(out.size); evals = C.c_uint64(0)
+        E = [C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.c_size_t]
+        self._call("em_match", [C.POINTER(EmParams)] + E + [C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_size_t] + E +
+                   [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)],
+                   C.byref(prm), _ptr(lx, C.c_uint16), _ptr(ly, C.c_uint16), _ptr(lt, C.c_int64), _ptr(lp, C.c_uint8), lx.size,
+                   _ptr(sc, C.c_int32), _ptr(sp, C.c_double), sc.size,
+                   _ptr(rx, C.c_uint16), _ptr(ry, C.c_uint16), _ptr(rt, C.c_int64), _ptr(rp, C.c_uint8), rx.size,
+                   out.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(evals))
+        return out[: n.value].copy(), evals.value
+
+    def seeds_to_points(self, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=SEED_DTYPE)
+        out = np.zeros(max(seeds.size, 1), DEPTH_POINT_DTYPE)
+        self._call("seeds_to_points", [C.c_void_p, C.c_size_t, C.c_void_p], seeds.ctypes.data_as(C.c_void_p), seeds.size,
+                   out.ctypes.data_as(C.c_void_p))
+        return out[: seeds.size].copy()
+
+    def naive_propagate(self, pts, T_world_frame, reset_map):
+        pts = np.ascontiguousarray(pts, dtype=DEPTH_POINT_DTYPE)
+        T = _arr(T_world_frame, np.float64)
+        self._call("naive_propagate", [C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.c_int],
+                   pts.ctypes.data_as(C.c_void_p), pts.size, _ptr(T, C.c_double), int(reset_map))
 
     def map_clean(self, var_thr, age_thr, rho_max, rho_min):
         self._call("map_clean", [C.c_double] * 4, var_thr, age_thr, rho_max, rho_min)

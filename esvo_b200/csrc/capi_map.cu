@@ -208,6 +208,44 @@ ESVO_API int esvo_fuse(esvo_ctx* c, const esvo_depth_point* pts, size_t n, const
   return rc;
 }
 
+// ---- comparison modes of esvo_MVStereo ----
+ESVO_API int esvo_em_match(esvo_ctx* c, const esvo_em_params* prm, const uint16_t* lx, const uint16_t* ly, const int64_t* lt, const uint8_t* lp,
+                           size_t nl, const int32_t* slice_counts, const double* slice_poses, size_t n_slices, const uint16_t* rx,
+                           const uint16_t* ry, const int64_t* rt, const uint8_t* rp, size_t nr, esvo_seed* out, size_t* n_seeds,
+                           uint64_t* n_evals) {
+  CHECK_CTX(c);
+  if (!prm || !n_seeds || (nl && (!lx || !ly || !lt || !lp)) || (nr && (!rx || !ry || !rt || !rp)) || (n_slices && (!slice_counts || !slice_poses)))
+    return ESVO_ERR_INVALID_ARG;
+  if (prm->patch_size_x < 1 || prm->patch_size_y < 1 || (*n_seeds && !out)) return ESVO_ERR_INVALID_ARG;
+  { int rc0 = drain(c); if (rc0) return rc0; }
+  if (!c->obs_set) return ESVO_ERR_STATE;
+  return em_match(c, prm, lx, ly, lt, lp, nl, slice_counts, slice_poses, n_slices, rx, ry, rt, rp, nr, out, n_seeds, n_evals);
+}
+ESVO_API int esvo_seeds_to_points(esvo_ctx* c, const esvo_seed* seeds, size_t n, esvo_depth_point* out) {
+  CHECK_CTX(c);
+  if (n && (!seeds || !out)) return ESVO_ERR_INVALID_ARG;
+  { int rc0 = drain(c); if (rc0) return rc0; }
+  return seeds_to_points(c, seeds, n, out);
+}
+ESVO_API int esvo_naive_propagate(esvo_ctx* c, const esvo_depth_point* pts, size_t n, const double T[16], int reset_map) {
+  CHECK_CTX(c);
+  if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }
+  if (n && !pts) return ESVO_ERR_INVALID_ARG;
+  int rc = ESVO_OK;
+  if (reset_map) { if (!T) return ESVO_ERR_INVALID_ARG; if ((rc = fuse_reset_map(c, T))) return rc; }
+  esvo_depth_point* tmp = nullptr;
+  if (n) {
+    ESVO_CUDA_TRY(c, dmalloc(&tmp, n));
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(tmp, pts, n * sizeof(esvo_depth_point), cudaMemcpyHostToDevice, c->stream));
+    rc = fuse_points(c, tmp, n, nullptr, 0, /*naive=*/1);
+    if (!rc) rc = fuse_finish(c, /*naive=*/true);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    if (!rc && e != cudaSuccess) { c->set_error(std::string("esvo_naive_propagate: ") + cudaGetErrorString(e)); rc = ESVO_ERR_CUDA; }
+  }
+  return rc;
+}
+
 ESVO_API int esvo_map_clean(esvo_ctx* c, double var_thr, double age_thr, double rmax, double rmin) {
   CHECK_CTX(c);
   if (c->depth > 1) { int rc0 = drain(c); if (rc0) return rc0; }

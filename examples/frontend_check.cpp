@@ -52,6 +52,20 @@ int main() {
     if (xyz.size() != 6 || xyz[0] != 3.f || xyz[1] != 7.f || xyz[2] != 10.f || nearp.size() != 3) bad |= 2048;
     (void)on;
   }
+  // eventSlicingForEM: 1 us apart events, 1 ms slices over [ev[0], ev[0] + 5.5 ms): 5 slices of 1001 events (the bound event
+  // belongs to the slice), contiguous, median stamp = the 500th event of the slice
+  {
+    std::vector<esvo::Event*> ptrs; for (auto& e : ev) ptrs.push_back(&e);
+    std::vector<esvo_core::core::EventSlice> sl;
+    int calls = 0;
+    eventSlicingForEM(ptrs, ev[0].ts, ev[0].ts + 5500000, 1e-3, [&](int64_t, esvo::Pose& T) { ++calls; T.fill(0); return true; }, sl);
+    if (sl.size() != 5 || calls != 5) bad |= 32768;
+    size_t at = 0;
+    for (auto& e : sl) {
+      if (e.numEvents_ != 1001 || (size_t)(e.it_begin_ - ptrs.begin()) != at || e.t_median_ != ev[at + 500].ts) bad |= 65536;
+      at += e.numEvents_;
+    }
+  }
   std::printf("frontend check %s (flags %d): %zu events, %zu stamps\n", bad ? "FAILED" : "ok", bad, sel.size(), st.size());
   return bad;
 }

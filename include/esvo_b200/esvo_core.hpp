@@ -39,6 +39,7 @@ class CameraSystem {
     ctx_ = esvo_create(device, &left, &right, &params, &st);
     if (!ctx_) throw std::runtime_error("esvo_create failed with status " + std::to_string(st) + " (no CPU fallback)");
     params_ = params; width_ = left.width; height_ = left.height;
+    std::copy(left.P, left.P + 12, P_left_);
     double d[4]; esvo_get_derived(ctx_, d); baseline_ = d[0];
   }
   ~CameraSystem() { esvo_destroy(ctx_); }
@@ -48,6 +49,7 @@ class CameraSystem {
   const esvo_params& params() const { return params_; }
   int width_ = 0, height_ = 0;
   double baseline_ = 0;
+  double P_left_[12] = {0};   // cam_left_ptr_->P_
  private:
   esvo_ctx* ctx_ = nullptr;
   esvo_params params_;
@@ -186,6 +188,11 @@ class DepthFusion {
     df->fresh_ = false;
     return nf;
   }
+  // naive_propagation (DepthFusion.cpp:232-288): nearest wins, no fusion -- the accumulation of the MVStereo comparison modes
+  void naive_propagation(std::vector<DepthPoint>& dp_obs, DepthFrame::Ptr& df) {
+    if (esvo_naive_propagate(camSysPtr_->ctx(), dp_obs.data(), dp_obs.size(), df->T_world_frame_.data(), df->fresh_ ? 1 : 0) == ESVO_OK)
+      df->fresh_ = false;
+  }
   // DepthMap::clean (SmartGrid.h:222-243) and the element list, exposed here because the map is ctx-resident
   void clean(double var_threshold, double age_threshold, double range_max, double range_min) {
     esvo_map_clean(camSysPtr_->ctx(), var_threshold, age_threshold, range_max, range_min);
@@ -207,6 +214,69 @@ class DepthRegularization {
   void apply() { esvo_map_regularize(camSysPtr_->ctx()); }
  private:
   CameraSystem::Ptr camSysPtr_;
+};
+
+// core::EventSlice (EventMatcher.h:17-28): a run of left events that shares one virtual-view pose
+struct EventSlice {
+  explicit EventSlice(double SLICE_THICKNESS = 2 * 1e-3) : SLICE_THICKNESS_(SLICE_THICKNESS) {}
+  size_t numEvents_ = 0;
+  double SLICE_THICKNESS_;
+  int64_t t_median_ = 0;
+  esvo::Pose transf_{};
+  std::vector<esvo::Event*>::iterator it_begin_, it_end_;
+};
+
+// core::EventMatcher (EventMatcher.h:30-100): the event-to-event matcher of [26] the reference keeps for comparison.
+class EventMatcher {
+ public:
+  EventMatcher(CameraSystem::Ptr camSysPtr, size_t numThread = 1, double Time_THRESHOLD = 10e-5, double EPIPOLAR_THRESHOLD = 0.5,
+               double TS_NCC_THRESHOLD = 0.1, size_t patch_size_X = 25, size_t patch_size_Y = 5, size_t patch_intensity_threshold = 125,
+               double patch_valid_ratio = 0.1)
+      : camSysPtr_(std::move(camSysPtr)), NUM_THREAD_(numThread) {
+    resetParameters(Time_THRESHOLD, EPIPOLAR_THRESHOLD, TS_NCC_THRESHOLD, patch_size_X, patch_size_Y, patch_intensity_threshold, patch_valid_ratio);
+  }
+  void resetParameters(double Time_THRESHOLD, double EPIPOLAR_THRESHOLD, double TS_NCC_THRESHOLD, size_t patch_size_X, size_t patch_size_Y,
+                       size_t patch_intensity_threshold, double patch_valid_ratio) {
+    prm_.time_threshold_s = Time_THRESHOLD; prm_.epipolar_threshold = EPIPOLAR_THRESHOLD; prm_.ts_ncc_threshold = TS_NCC_THRESHOLD;
+    prm_.patch_size_x = (int32_t)patch_size_X; prm_.patch_size_y = (int32_t)patch_size_Y; prm_.num_thread = (int32_t)NUM_THREAD_; prm_._pad = 0;
+    patch_intensity_threshold_ = patch_intensity_threshold; patch_valid_ratio_ = patch_valid_ratio;   // unused by the reference as well
+  }
+  void createMatchProblem(esvo::StampedTimeSurfaceObs* pTS_obs, std::vector<EventSlice>* vEventSlice_ptr, std::vector<esvo::Event*>* vEventPtr_cand) {
+    pTS_obs_ = pTS_obs; pvEventSlice_ = vEventSlice_ptr; pvCandEventPtr_ = vEventPtr_cand;
+  }
+  void match_all_HyperThread(std::vector<EventMatchPair>& vEMP) {
+    vEMP.clear();
+    if (!pTS_obs_ || !pvEventSlice_ || !pvCandEventPtr_ || pvEventSlice_->empty()) return;
+    const auto& obs = pTS_obs_->second;
+    if (esvo_set_ts_pair(camSysPtr_->ctx(), obs.left, obs.right, obs.tr_.data()) != ESVO_OK) return;
+    // the events of all slices are contiguous from the first slice's begin (match(), EventMatcher.cpp:233-251)
+    std::vector<int32_t> counts; std::vector<double> poses; size_t total = 0;
+    for (auto& es : *pvEventSlice_) { counts.push_back((int32_t)es.numEvents_); poses.insert(poses.end(), es.transf_.begin(), es.transf_.end()); total += es.numEvents_; }
+    std::vector<uint16_t> lx, ly, rx, ry; std::vector<int64_t> lt, rt; std::vector<uint8_t> lp, rp;
+    auto it = (*pvEventSlice_)[0].it_begin_;
+    for (size_t i = 0; i < total; ++i, ++it) { lx.push_back((*it)->x); ly.push_back((*it)->y); lt.push_back((*it)->ts); lp.push_back((*it)->polarity); }
+    for (auto* e : *pvCandEventPtr_) { rx.push_back(e->x); ry.push_back(e->y); rt.push_back(e->ts); rp.push_back(e->polarity); }
+    vEMP.resize(total);
+    size_t n = total;
+    if (esvo_em_match(camSysPtr_->ctx(), &prm_, lx.data(), ly.data(), lt.data(), lp.data(), total, counts.data(), poses.data(), counts.size(),
+                      rx.data(), ry.data(), rt.data(), rp.data(), rx.size(), vEMP.data(), &n, &n_evals_) != ESVO_OK)
+      n = 0;
+    vEMP.resize(n);
+  }
+  // plain event order.  (The reference's single-thread walk additionally stops one event short of every slice's end,
+  // EventMatcher.cpp:165-183; esvo_MVStereo only calls the HyperThread form, so that quirk is not reproduced.)
+  void match_all_SingleThread(std::vector<EventMatchPair>& vEMP) {
+    const int32_t nt = prm_.num_thread; prm_.num_thread = 1; match_all_HyperThread(vEMP); prm_.num_thread = nt;
+  }
+  uint64_t n_evals_ = 0;
+ private:
+  CameraSystem::Ptr camSysPtr_;
+  size_t NUM_THREAD_;
+  esvo_em_params prm_{};
+  size_t patch_intensity_threshold_ = 125; double patch_valid_ratio_ = 0.1;
+  esvo::StampedTimeSurfaceObs* pTS_obs_ = nullptr;
+  std::vector<EventSlice>* pvEventSlice_ = nullptr;
+  std::vector<esvo::Event*>* pvCandEventPtr_ = nullptr;
 };
 
 // core::RefFrame / CurFrame (RegProblemLM.h:58-74)
@@ -350,6 +420,34 @@ inline void packPointCloud(const std::vector<esvo::DepthPoint>& elems, const esv
       for (int k = 0; k < 3; ++k) xyz_near->push_back((float)w[k]);
   }
 }
+//  * eventSlicingForEM (esvo_MVStereo.cpp:1008-1040): cuts the time-ordered left events of [t_lowBound, t_upBound) into
+//    floor((t_up - t_low) / EM_Slice_Thickness) slices; a slice runs from its first event to lower_bound(first stamp +
+//    thickness) INCLUSIVE, the next one starts behind it; its pose is the trajectory at the median event's stamp.
+template <class PoseAt>
+inline void eventSlicingForEM(std::vector<esvo::Event*>& vEventsPtr_left, int64_t t_lowBound_ns, int64_t t_upBound_ns, double EM_Slice_Thickness,
+                              PoseAt&& getPoseAt, std::vector<core::EventSlice>& eventSlices) {
+  eventSlices.clear();
+  if (vEventsPtr_left.empty()) return;
+  const size_t numSlice = (size_t)std::floor((toSec(t_upBound_ns) - toSec(t_lowBound_ns)) / EM_Slice_Thickness);
+  auto it_tmp = vEventsPtr_left.begin();
+  for (size_t i = 0; i < numSlice; ++i) {
+    core::EventSlice es(EM_Slice_Thickness);
+    es.it_begin_ = it_tmp;
+    const double t_end = toSec(fromSec(toSec((*it_tmp)->ts) + es.SLICE_THICKNESS_));
+    es.it_end_ = std::lower_bound(vEventsPtr_left.begin(), vEventsPtr_left.end(), t_end,
+                                  [](const esvo::Event* e, double t) { return toSec(e->ts) < t; });   // tools::EventVecPtr_lower_bound (utils.h:43-48)
+    if (es.it_end_ == vEventsPtr_left.end()) --es.it_end_;
+    es.numEvents_ = (size_t)std::distance(es.it_begin_, es.it_end_) + 1;
+    auto it_median = es.it_begin_;
+    std::advance(it_median, es.numEvents_ / 2);
+    es.t_median_ = (*it_median)->ts;
+    getPoseAt(es.t_median_, es.transf_);
+    eventSlices.push_back(es);
+    it_tmp = es.it_end_;
+    ++it_tmp;
+    if (it_tmp == vEventsPtr_left.end()) break;
+  }
+}
 }  // namespace frontend
 
 // esvo_core::esvo_Mapping::MappingAtTime (esvo_Mapping.cpp:261-399) as one call with device-resident hand-off.
@@ -400,6 +498,143 @@ class esvo_Mapping {
   void reset() { esvo_mapping_reset(cs_->ctx()); }
  private:
   esvo::CameraSystem::Ptr cs_;
+};
+
+// esvo_core::esvo_MVStereo::MappingAtTime (esvo_MVStereo.cpp:239-520): the known-pose multi-view-stereo node the reference
+// uses to compare five depth estimators on the same fusion back-end.  The node's dataTransferring (:544-668) fills the
+// public input members below (front-end helpers: frontend::selectCloseEvents / samplePoseStamps / eventSlicingForEM);
+// MappingAtTime then runs the selected mode on the device through the same ABI entry points the mapper uses.
+class esvo_MVStereo {
+ public:
+  enum eMVStereoMode { PURE_EVENT_MATCHING, PURE_BLOCK_MATCHING, EM_PLUS_ESTIMATION, BM_PLUS_ESTIMATION, PURE_SEMI_GLOBAL_MATCHING };   // esvo_MVStereo.h:38-45
+  using PoseProvider = std::function<bool(int64_t, esvo::Pose&)>;
+  esvo_MVStereo(esvo::CameraSystem::Ptr cs, eMVStereoMode msm, size_t NUM_THREAD_MAPPING = 4)
+      : msm_(msm), em_(cs, NUM_THREAD_MAPPING), ebm_(cs), dpSolver_(cs), dFusor_(cs), dRegularizor_(cs), cs_(cs) {
+    const esvo_params& p = cs_->params();
+    em_.resetParameters(EM_Time_THRESHOLD_, EM_EPIPOLAR_THRESHOLD_, EM_TS_NCC_THRESHOLD_, (size_t)p.patch_size_x, (size_t)p.patch_size_y, 125, 0.1);   // :85-91
+    maxNumFusionFrames_ = (size_t)p.max_num_fusion_frames; maxNumFusionPoints_ = (size_t)p.max_num_fusion_points;
+  }
+  void setPoseProvider(PoseProvider f) { getPoseAt_ = std::move(f); }
+  void resetEMParameters(double thickness, double time_thr, double epi_thr, double ncc_thr) {
+    EM_Slice_Thickness_ = thickness; EM_Time_THRESHOLD_ = time_thr; EM_EPIPOLAR_THRESHOLD_ = epi_thr; EM_TS_NCC_THRESHOLD_ = ncc_thr;
+    const esvo_params& p = cs_->params();
+    em_.resetParameters(time_thr, epi_thr, ncc_thr, (size_t)p.patch_size_x, (size_t)p.patch_size_y, 125, 0.1);
+  }
+  // ---- inputs, as dataTransferring leaves them (:544-668) ----
+  esvo::StampedTimeSurfaceObs TS_obs_;
+  std::vector<esvo::Event*> vEventsPtr_left_, vEventsPtr_right_;        // EM: all events of [t_lowBound_, t_upBound_)
+  int64_t t_lowBound_ = 0, t_upBound_ = 0;
+  std::vector<esvo::Event*> vCloseEventsPtr_left_;                       // BM: newest-first window events (already denoised / truncated)
+  esvo::StampTransformationMap st_map_;
+  std::vector<esvo::Event*> vEventsPtr_left_SGM_;                        // SGM: events that draw the edge mask
+  // ---- results ----
+  std::vector<esvo::EventMatchPair> vEMP_;
+  std::deque<std::vector<esvo::DepthPoint>> dqvDepthPoints_;
+  size_t numFusionCount_ = 0;
+
+  bool MappingAtTime() {
+    const esvo_params& p = cs_->params();
+    core::DepthFrame::Ptr depthFramePtr_new = std::make_shared<core::DepthFrame>();             // :246-251
+    depthFramePtr_new->setId(TS_obs_.second.id_);
+    depthFramePtr_new->setTransformation(TS_obs_.second.tr_);
+    depthFramePtr_ = depthFramePtr_new;
+    vEMP_.clear();
+    if (msm_ == PURE_EVENT_MATCHING || msm_ == EM_PLUS_ESTIMATION) {                            // :257-306
+      std::vector<core::EventSlice> eventSlices;
+      frontend::eventSlicingForEM(vEventsPtr_left_, t_lowBound_, t_upBound_, EM_Slice_Thickness_,
+                                  [&](int64_t t, esvo::Pose& T) { return getPoseAt_ ? getPoseAt_(t, T) : false; }, eventSlices);
+      em_.createMatchProblem(&TS_obs_, &eventSlices, &vEventsPtr_right_);
+      em_.match_all_HyperThread(vEMP_);
+      if (vEMP_.empty()) return false;
+      if (msm_ == PURE_EVENT_MATCHING) { std::vector<esvo::DepthPoint> vdp; vEMP2vDP(vEMP_, vdp); return accumulateNaive(vdp); }
+    }
+    if (msm_ == PURE_SEMI_GLOBAL_MATCHING) {                                                    // :311-378
+      std::vector<int16_t> dispMap((size_t)cs_->width_ * cs_->height_);
+      if (esvo_set_ts_pair(cs_->ctx(), TS_obs_.second.left, TS_obs_.second.right, TS_obs_.second.tr_.data()) != ESVO_OK) return false;
+      if (esvo_sgbm_compute(cs_->ctx(), nullptr, nullptr, (int)num_disparities_, (int)block_size_, (int)P1_, (int)P2_, -1, 0, 11, dispMap.data()) != ESVO_OK)
+        return false;
+      std::vector<esvo::DepthPoint> vdp_sgm;
+      sgmPoints(dispMap, vdp_sgm);
+      return accumulateNaive(vdp_sgm);
+    }
+    if (msm_ == PURE_BLOCK_MATCHING || msm_ == BM_PLUS_ESTIMATION) {                            // :383-431
+      ebm_.createMatchProblem(&TS_obs_, &st_map_, &vCloseEventsPtr_left_);
+      ebm_.match_all_HyperThread(vEMP_);
+      if (msm_ == PURE_BLOCK_MATCHING) { std::vector<esvo::DepthPoint> vdp; vEMP2vDP(vEMP_, vdp); return accumulateNaive(vdp); }
+    }
+    // EM_PLUS_ESTIMATION / BM_PLUS_ESTIMATION: nonlinear optimisation, culling, fusion, clean, regularisation (:437-507)
+    std::vector<esvo::DepthPoint> vdp;
+    dpSolver_.solve(&vEMP_, &TS_obs_, vdp);
+    dpSolver_.pointCulling(vdp, p.stdvar_vis_threshold, p.residual_vis_threshold * p.residual_vis_threshold * p.patch_size_x * p.patch_size_y,
+                           p.invdepth_min_range, p.invdepth_max_range);
+    dqvDepthPoints_.push_back(vdp);
+    if (p.fusion_strategy == ESVO_FUSION_CONST_POINTS) {
+      auto total = [&] { size_t n = 0; for (auto& v : dqvDepthPoints_) n += v.size(); return n; };
+      while ((double)total() > 1.5 * (double)maxNumFusionPoints_) dqvDepthPoints_.pop_front();
+    } else {
+      while (dqvDepthPoints_.size() > maxNumFusionFrames_) dqvDepthPoints_.pop_front();
+    }
+    numFusionCount_ = 0;
+    for (auto it = dqvDepthPoints_.rbegin(); it != dqvDepthPoints_.rend(); ++it) numFusionCount_ += (size_t)dFusor_.update(*it, depthFramePtr_, p.fusion_radius);
+    dFusor_.clean(p.stdvar_vis_threshold * p.stdvar_vis_threshold, p.age_vis_threshold, p.invdepth_max_range, p.invdepth_min_range);
+    if (p.regularization) dRegularizor_.apply();
+    return true;
+  }
+  // vEMP2vDP (:1072-1097)
+  void vEMP2vDP(std::vector<esvo::EventMatchPair>& vEMP, std::vector<esvo::DepthPoint>& vdp) {
+    vdp.resize(vEMP.size());
+    if (esvo_seeds_to_points(cs_->ctx(), vEMP.data(), vEMP.size(), vdp.data()) != ESVO_OK) vdp.clear();
+  }
+  void getElements(std::vector<esvo::DepthPoint>& out) { dFusor_.getElements(out); }
+  void reset() { dqvDepthPoints_.clear(); }
+  eMVStereoMode msm_;
+  double EM_Slice_Thickness_ = 1e-3, EM_Time_THRESHOLD_ = 5e-5, EM_EPIPOLAR_THRESHOLD_ = 0.5, EM_TS_NCC_THRESHOLD_ = 0.1;   // :81-84
+  size_t num_disparities_ = 16 * 3, block_size_ = 11, P1_ = 8 * 11 * 11, P2_ = 32 * 11 * 11;                                // :100-107
+  size_t maxNumFusionFrames_ = 20, maxNumFusionPoints_ = 2000;
+ private:
+  // accumulation of modes 0, 1, 4 (:280-286,355-361,423-427): window of maxNumFusionFrames_ vectors, newest first, nearest wins
+  bool accumulateNaive(std::vector<esvo::DepthPoint>& vdp) {
+    dqvDepthPoints_.push_back(vdp);
+    while (dqvDepthPoints_.size() > maxNumFusionFrames_) dqvDepthPoints_.pop_front();
+    for (auto it = dqvDepthPoints_.rbegin(); it != dqvDepthPoints_.rend(); ++it) dFusor_.naive_propagation(*it, depthFramePtr_);
+    return true;
+  }
+  // the PURE_SEMI_GLOBAL_MATCHING branch between the SGM call and the accumulation (:320-352) with createEdgeMask
+  // (undistorted events, radius 0, :1130-1175) inlined: one Gaussian point per event whose rectified pixel lies right of
+  // numDisparities and carries a non-negative disparity
+  void sgmPoints(const std::vector<int16_t>& dispMap, std::vector<esvo::DepthPoint>& vdp_sgm) {
+    const int W = cs_->width_, H = cs_->height_;
+    if (lut_.empty()) { lut_.resize((size_t)2 * W * H); esvo_get_rectify_tables(cs_->ctx(), 0, nullptr, nullptr, lut_.data(), nullptr); }
+    double d[4]; esvo_get_derived(cs_->ctx(), d);
+    std::vector<esvo::EventMatchPair> pseudo;
+    for (auto* e : vEventsPtr_left_SGM_) {
+      const double* coor = &lut_[2 * ((size_t)e->y * W + e->x)];
+      const int x = (int)std::floor(coor[0]), y = (int)std::floor(coor[1]);
+      if (x < 0 || x >= W || y < 0 || y >= H) continue;
+      if ((size_t)x < num_disparities_) continue;
+      const double disp = dispMap[(size_t)y * W + x] / 16.0;
+      if (disp < 0) continue;
+      esvo::EventMatchPair s{};
+      s.x_left[0] = x * 1.0; s.x_left[1] = y * 1.0;
+      s.inv_depth = disp / (cs_->P_left_[0] * d[0]);
+      s.cost = 0.0;
+      std::copy(TS_obs_.second.tr_.begin(), TS_obs_.second.tr_.end(), s.T_world_virtual);
+      pseudo.push_back(s);
+    }
+    vEMP2vDP(pseudo, vdp_sgm);
+    for (size_t i = 0; i < vdp_sgm.size(); ++i) {       // DepthPoint dp(x, y): the reference passes (x, y) as (row, col) (:336)
+      vdp_sgm[i].row = (int32_t)pseudo[i].x_left[0]; vdp_sgm[i].col = (int32_t)pseudo[i].x_left[1];
+    }
+  }
+  core::EventMatcher em_;
+  core::EventBM ebm_;
+  core::DepthProblemSolver dpSolver_;
+  core::DepthFusion dFusor_;
+  core::DepthRegularization dRegularizor_;
+  esvo::CameraSystem::Ptr cs_;
+  core::DepthFrame::Ptr depthFramePtr_;
+  PoseProvider getPoseAt_;
+  std::vector<double> lut_;
 };
 
 // esvo_core::esvo_Tracking (esvo_Tracking.h:51-53; esvo_Tracking.cpp:79-265 TrackingLoop / refDataTransferring /

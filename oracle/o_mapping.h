@@ -603,12 +603,14 @@ struct DepthFusion {
   // fusion (:90-192)
   int fusion(const DepthPoint& prop, DepthMap& dm, int radius) const {
     int numFusion = 0;
-    int rr[9], cc[9], n = 0;
-    if (radius == 0) { for (int dy = 0; dy <= 1; ++dy) for (int dx = 0; dx <= 1; ++dx) { rr[n] = (int)prop.row + dy; cc[n] = (int)prop.col + dx; n++; } }
-    else { for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) { rr[n] = (int)prop.row + dy; cc[n] = (int)prop.col + dx; n++; } }
+    // 64-bit coordinates: a NaN re-projection passes boundaryCheck(double) and becomes row = col = 2^63 through x86-64's
+    // double -> size_t conversion, which the per-pixel boundaryCheck below then rejects (never truncate it to 32 bits)
+    int64_t rr[9], cc[9]; int n = 0;
+    if (radius == 0) { for (int dy = 0; dy <= 1; ++dy) for (int dx = 0; dx <= 1; ++dx) { rr[n] = prop.row + dy; cc[n] = prop.col + dx; n++; } }
+    else { for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) { rr[n] = prop.row + dy; cc[n] = prop.col + dx; n++; } }
     for (int i = 0; i < n; ++i) {
-      int row = rr[i], col = cc[i];
-      if (row < 0 || col < 0 || !boundaryCheck(col, row, cs->left.W, cs->left.H)) continue;  // size_t wrap == out of range
+      if (rr[i] < 0 || cc[i] < 0 || rr[i] >= cs->left.H || cc[i] >= cs->left.W) continue;  // size_t wrap == out of range
+      int row = (int)rr[i], col = (int)cc[i];
       if (!dm.exists(row, col)) {
         DepthPoint nw(row, col);
         if (lsnorm == ESVO_LSNORM_L2) nw.update(prop.invDepth, prop.variance);
@@ -669,8 +671,9 @@ struct DepthFusion {
       if (!naive_propagate_one_point(o, prop, T_frame_obs)) continue;
       for (int dy = 0; dy <= 1; ++dy)
         for (int dx = 0; dx <= 1; ++dx) {
-          int row = (int)prop.row + dy, col = (int)prop.col + dx;
-          if (!boundaryCheck(col, row, cs->left.W, cs->left.H)) continue;
+          const int64_t row64 = prop.row + dy, col64 = prop.col + dx;   // 64-bit: see fusion()
+          if (row64 < 0 || col64 < 0 || row64 >= cs->left.H || col64 >= cs->left.W) continue;
+          int row = (int)row64, col = (int)col64;
           if (!dm.exists(row, col)) {                       // case 1
             DepthPoint nw(row, col);
             nw.update(prop.invDepth, prop.variance);

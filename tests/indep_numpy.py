@@ -289,3 +289,107 @@ def pack_point_cloud(p_cam, T_world_frame):
     """publishPointCloud (:909-953): p_world = R p_cam + t as pcl::PointXYZ (f32), DepthMap iteration order."""
     T = np.asarray(T_world_frame, float).reshape(4, 4)
     return (np.asarray(p_cam) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+
+
+# ---- comparison modes of esvo_MVStereo: EventMatcher [26] (esvo_core/src/core/EventMatcher.cpp) ----
+def em_zncc_cost(pl, pr):
+    """EventMatcher::zncc_cost (:253-274): mean-free patches divided by (Frobenius norm + 1e-6)."""
+    pl = np.asarray(pl, np.float64); pr = np.asarray(pr, np.float64)
+    ls = pl - pl.mean(); rs = pr - pr.mean()
+    ln = ls / (np.linalg.norm(ls) + 1e-6); rn = rs / (np.linalg.norm(rs) + 1e-6)
+    return 0.5 * (1.0 - float((ln * rn).sum()))
+
+
+def event_slicing_for_em(t_left, t_low_ns, t_up_ns, slice_thickness):
+    """esvo_MVStereo::eventSlicingForEM (esvo_MVStereo.cpp:1008-1040) over the time-ordered left events vEventsPtr_left_:
+    numSlice = floor((t_up - t_low) / thickness); a slice runs from its first event to lower_bound(first stamp + thickness)
+    INCLUSIVE (the iterator itself belongs to the slice; end() steps back one), the next one starts behind it.
+    Returns (counts, median stamps)."""
+    t_left = np.asarray(t_left, np.int64)
+    secs = np.array([ros_to_sec(t) for t in t_left])
+    num = int(np.floor((ros_to_sec(t_up_ns) - ros_to_sec(t_low_ns)) / slice_thickness))
+    counts, med = [], []
+    it = 0
+    for _ in range(num):
+        t_end = ros_to_sec(ros_from_sec(secs[it] + slice_thickness))
+        it_end = int(np.searchsorted(secs, t_end, side="left"))
+        if it_end == t_left.size:
+            it_end -= 1
+        n = it_end - it + 1
+        counts.append(n); med.append(int(t_left[it + n // 2]))
+        it = it_end + 1
+        if it == t_left.size:
+            break
+    return np.array(counts, np.int32), np.array(med, np.int64)
+
+
+def event_match(left, right, slice_counts, slice_poses, lut_l, lut_r, Pl, Pr, baseline, ts_l, ts_r, T_world_left,
+                time_thr, epi_thr, ncc_thr, wx, wy, num_thread):
+    """EventMatcher::match_all_HyperThread / match / match_an_event (:60-163,185-251).  left / right: dicts of x, y, t, p
+    (right time-ordered).  Returns a list of dicts in the reference's thread-major order and the number of zncc evaluations."""
+    H, W = ts_l.shape
+    tsl = ts_l.astype(np.float64); tsr = ts_r.astype(np.float64)
+    slice_of = np.repeat(np.arange(len(slice_counts)), slice_counts)
+    total = min(slice_of.size, left["x"].size)
+    r_secs = np.array([ros_to_sec(t) for t in right["t"]])
+    T_left_world = np.linalg.inv(np.asarray(T_world_left, float).reshape(4, 4))
+    hx, hy = (wx - 1) // 2, (wy - 1) // 2
+    evals = 0
+
+    def one(i):
+        nonlocal evals
+        te = ros_to_sec(left["t"][i])
+        low = ros_to_sec(ros_from_sec(te - time_thr / 2)); up = ros_to_sec(ros_from_sec(te + time_thr / 2))
+        b = int(np.searchsorted(r_secs, low, side="left")); e = int(np.searchsorted(r_secs, up, side="left"))
+        cand = [j for j in range(b, e) if low <= r_secs[j] <= up and bool(right["p"][j]) == bool(left["p"][i])]     # temporal + polarity (:66-88)
+        if not cand:
+            return None
+        xl = lut_l[int(left["y"][i]), int(left["x"][i])]
+        epi = []
+        for j in cand:                                                                                               # epipolar (:93-108)
+            xr = lut_r[int(right["y"][j]), int(right["x"][j])]
+            if abs(xl[1] - xr[1]) <= epi_thr and xr[0] < xl[0]:
+                epi.append((j, xr))
+        if not epi:
+            return None
+        T_world_rv = np.asarray(slice_poses[slice_of[i]], float).reshape(4, 4)
+        T_left_rv = T_left_world @ T_world_rv
+        f = Pl[0, 0]
+        min_cost, best, best_depth = 1.0, 0, 0.0
+        for q, (j, xr) in enumerate(epi):                                                                            # motion check (:110-150)
+            depth = baseline * f / (xl[0] - xr[0])
+            p_rv = cam2world(Pl, xl, 1.0 / depth)
+            p_left = T_left_rv[:3, :3] @ p_rv + T_left_rv[:3, 3]
+            h1 = Pl[:, :3] @ p_left + Pl[:, 3]; h2 = Pr[:, :3] @ p_left + Pr[:, 3]
+            x1 = h1[:2] / h1[2]; x2 = h2[:2] / h2[2]
+            if any(xs[0] < hx or xs[0] > W - hx or xs[1] < hy or xs[1] > H - hy for xs in (x1, x2)):               # warping2 (:276-306)
+                continue
+            pa = patch_interpolation(tsl, x1, wx, wy)
+            pb = patch_interpolation(tsr, x2, wx, wy) if pa is not None else None
+            if pa is None or pb is None:
+                continue
+            cost = em_zncc_cost(pa, pb); evals += 1
+            if cost < min_cost:
+                min_cost, best, best_depth = cost, q, depth
+        if min_cost > ncc_thr:
+            return None
+        with np.errstate(divide="ignore"):
+            inv = np.float64(1.0) / np.float64(best_depth)
+        return dict(i=i, j=epi[best][0], x_left=xl, x_right=epi[best][1], t_ns=int(left["t"][i]), T=T_world_rv, inv_depth=float(inv), cost=min_cost)
+
+    out = []
+    for tid in range(num_thread):
+        for i in range(tid, total, num_thread):
+            m = one(i)
+            if m is not None:
+                out.append(m)
+    return out, evals
+
+
+def vemp_to_points(matches, Pl, age_vis_threshold):
+    """esvo_MVStereo::vEMP2vDP (esvo_MVStereo.cpp:1072-1097)."""
+    out = []
+    for m in matches:
+        out.append(dict(row=int(np.floor(m["x_left"][1])), col=int(np.floor(m["x_left"][0])), x=m["x_left"], inv_depth=m["inv_depth"],
+                        variance=1e-6, residual=m["cost"], age=int(age_vis_threshold), p_cam=cam2world(Pl, m["x_left"], m["inv_depth"]), T=m["T"]))
+    return out

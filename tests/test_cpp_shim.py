@@ -131,3 +131,62 @@ def test_shim_mapping_to_tracking_matches_oracle(oracle_lib, product_lib, tmp_pa
     assert np.abs(T_idle - To2).max() < 1e-6
     # numEventsSinceLastObs_ = distance(lower_bound(old cur stamp = 0), lower_bound(t_cur)) + 1 (:241-243)
     assert hdr[6] == int(np.searchsorted(L["t"], s2["t_ts_ns"], side="left")) + 1
+
+
+@pytest.mark.gpu
+def test_shim_mvstereo_modes_match_oracle(oracle_lib, product_lib, tmp_path):
+    """examples/mvstereo_modes.cpp: esvo_core::esvo_MVStereo::MappingAtTime in its five MVStereoMode settings (event matcher [26],
+    block matching, EM + optimisation, BM + optimisation = the ESVO mapper, SGM) through the C++ shim on the GPU, one frame each,
+    against the same sequences on the oracle (tests/test_gpu_mvstereo.py::_run_mode; cv2.StereoSGBM feeds the oracle's SGM mode)."""
+    import struct
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    from esvo_b200 import capi, configs
+    from test_gpu_mvstereo import _run_mode
+    from util import build_ts_pair, em_problem, make_backends, scenario
+    build = os.path.join(ROOT, "esvo_b200", "_build")
+    exe = str(tmp_path / "mvstereo_modes")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "mvstereo_modes.cpp"),
+                           "-L" + build, "-lesvo_b200", "-Wl,-rpath," + build, "-o", exe])
+    s = dict(scenario("hkust", seed=4, n_seeds=800, t_ts=0.5))
+    s["Pl00"] = configs.rig_arrays("hkust")["left"]["P"][0, 0]
+    o, g = make_backends("hkust", oracle_lib, product_lib)
+    g.close()
+    tl, tr = build_ts_pair(o, s)
+    o.ts_reset(0); o.ts_reset(1)
+    left, right, counts, poses = em_problem(s)
+    t_up = s["t_ts_ns"]; t_low = t_up - int(4.0 * 1e6)
+    import indep_numpy as ind
+    _, med = ind.event_slicing_for_em(left["t"], t_low, t_up, 1e-3)
+    Tw = np.ascontiguousarray(s["T_world_left"], np.float64)
+    sd = s["seeds"]
+    scen = tmp_path / "scen.bin"; resf = tmp_path / "res.bin"
+    with open(scen, "wb") as f:
+        f.write(struct.pack("<ii", o.W, o.H)); f.write(struct.pack("<qqq", s["t_ts_ns"], t_low, t_up)); f.write(Tw.tobytes())
+        f.write(tl.tobytes()); f.write(tr.tobytes())
+        for e in (left, right):
+            f.write(struct.pack("<i", e["x"].size))
+            for a, dt in ((e["x"], np.uint16), (e["y"], np.uint16), (e["t"], np.int64), (e["p"], np.uint8)):
+                f.write(np.ascontiguousarray(a, dt).tobytes())
+        f.write(struct.pack("<i", sd["x"].size))
+        for a, dt in ((sd["x"], np.uint16), (sd["y"], np.uint16), (sd["t"], np.int64)):
+            f.write(np.ascontiguousarray(a, dt).tobytes())
+        f.write(struct.pack("<i", s["pose_t"].size)); f.write(np.ascontiguousarray(s["pose_t"], np.int64).tobytes())
+        f.write(np.ascontiguousarray(s["poses"], np.float64).tobytes())
+        f.write(struct.pack("<i", med.size)); f.write(np.ascontiguousarray(med, np.int64).tobytes())
+        f.write(np.ascontiguousarray(poses, np.float64).tobytes())
+    p = subprocess.run([exe, str(scen), str(resf)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    raw = open(resf, "rb").read()
+    rec = np.dtype([("row", "<i4"), ("col", "<i4"), ("inv_depth", "<f8"), ("variance", "<f8"), ("residual", "<f8"), ("age", "<i8")])
+    off = 0
+    d_ref = cv2.StereoSGBM_create(0, 48, 11, 8 * 121, 32 * 121, -1, 0, 11).compute(tl, tr)
+    for mode in range(5):
+        n_match, n_map = struct.unpack_from("<ii", raw, off); off += 8
+        m = np.frombuffer(raw, rec, n_map, off); off += n_map * rec.itemsize
+        o.set_ts_pair(tl, tr, Tw)
+        mo = _run_mode(o, mode, s, [], 20, d_ref)
+        assert n_map == mo.size and n_map > 20, (mode, n_map, mo.size, p.stdout)
+        assert np.array_equal(m["row"], mo["row"]) and np.array_equal(m["col"], mo["col"]) and np.array_equal(m["age"], mo["age"]), mode
+        r = np.abs(m["inv_depth"] - mo["inv_depth"]) / np.abs(mo["inv_depth"])
+        assert (r < 1e-4).mean() > 0.995 and np.median(r) < 1e-7, (mode, np.median(r), r.max())

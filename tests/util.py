@@ -42,3 +42,24 @@ def build_ts_pair(b, s):
 def rel(a, b):
     a = np.asarray(a, float); b = np.asarray(b, float)
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def em_problem(s, window_ms=4.0, slice_thickness=1e-3, max_events=3000):
+    """The inputs esvo_MVStereo hands its EventMatcher (esvo_MVStereo.cpp:579-608,1008-1040): the left / right events of the
+    window before the observation stamp (at most EM_NUM_EVENT_MATCHING + 1 each), the left ones cut into slices of
+    EM_Slice_Thickness with the pose at each slice's median stamp."""
+    import indep_numpy as ind
+    t_up = s["t_ts_ns"]; t_low = t_up - int(window_ms * 1e6)
+
+    def window(e):
+        lo = int(np.searchsorted(e["t"], t_low, side="left")); hi = int(np.searchsorted(e["t"], t_up, side="left")) - 1
+        hi = min(hi, lo + max_events + 1)
+        return {k: e[k][lo:hi].copy() for k in ("x", "y", "t", "p")}
+    left, right = window(s["left"]), window(s["right"])
+    counts, med = ind.event_slicing_for_em(left["t"], t_low, t_up, slice_thickness)
+    poses = []
+    for t in med:
+        T = synth.pose_at(t * 1e-9)
+        T[:3, 3] *= 1.0 if s["rig"] == "hkust" else 20.0     # synth.make_stream's scene scale
+        poses.append(T.ravel())
+    return left, right, counts, np.array(poses)
