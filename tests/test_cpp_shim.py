@@ -190,3 +190,77 @@ def test_shim_mvstereo_modes_match_oracle(oracle_lib, product_lib, tmp_path):
         assert np.array_equal(m["row"], mo["row"]) and np.array_equal(m["col"], mo["col"]) and np.array_equal(m["age"], mo["age"]), mode
         r = np.abs(m["inv_depth"] - mo["inv_depth"]) / np.abs(mo["inv_depth"])
         assert (r < 1e-4).mean() > 0.995 and np.median(r) < 1e-7, (mode, np.median(r), r.max())
+
+
+def _nccl_build(exe):
+    build = os.path.join(ROOT, "esvo_b200", "_build")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+                           os.path.join(ROOT, "examples", "multi_stream_nccl.cpp"), "-L" + build, "-lesvo_b200", "-Wl,-rpath," + build,
+                           "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl", "-lpthread", "-o", exe])
+
+
+def test_multi_stream_nccl_example_compiles(product_lib, tmp_path):
+    """examples/multi_stream_nccl.cpp (C++ host, one thread per GPU, ncclAllGather of the stream records): builds against the
+    system NCCL; without a GPU it stops before any work."""
+    if not os.path.exists("/usr/include/nccl.h"):
+        pytest.skip("no system NCCL headers")
+    exe = str(tmp_path / "multi_stream_nccl")
+    _nccl_build(exe)
+    if has_gpu():
+        return
+    p = subprocess.run([exe, "/dev/null"], capture_output=True, text=True)
+    assert p.returncode == 2 and "no CPU fallback" in p.stdout
+
+
+@pytest.mark.gpu
+def test_multi_stream_nccl_gather_matches_python_records(oracle_lib, product_lib, tmp_path):
+    """The C++ multi-stream host: every visible GPU runs its own stream (rank r drops 200 r events from the selection budget),
+    the records travel through ONE ncclAllGather; each record equals what the Python binding computes for the same stream
+    (esvo_b200/dist.py layout and checksum)."""
+    import struct
+    import numpy as np
+    import indep_numpy as ind
+    from esvo_b200 import capi, configs, dist as edist, synth
+    if not os.path.exists("/usr/include/nccl.h"):
+        pytest.skip("no system NCCL headers")
+    exe = str(tmp_path / "multi_stream_nccl")
+    _nccl_build(exe)
+    s = synth.make_stream("hkust", seed=2, n_seeds=5000, t_ts=0.5)
+    l, r = configs.rig_calibs("hkust")
+    o = capi.Backend(oracle_lib, l, r, configs.params_for("hkust", oracle_lib))
+    for cam, side in ((0, "left"), (1, "right")):
+        e = s[side]; o.ts_push_events(cam, e["x"], e["y"], e["t"], e["p"])
+    _, tl = o.ts_build(0, s["t_ts_ns"], want_idx=False); _, tr = o.ts_build(1, s["t_ts_ns"], want_idx=False)
+    W, H = o.W, o.H
+    half_slice, pen, frames = 0.001, 3000, 2
+    L = s["left"]
+    Tw = np.ascontiguousarray(s["T_world_left"], np.float64)
+    scen = tmp_path / "scen.bin"
+    with open(scen, "wb") as f:
+        f.write(struct.pack("<iii", W, H, 0)); f.write(struct.pack("<qq", s["t_ts_ns"], s["t_ts_ns"])); f.write(Tw.tobytes())
+        f.write(struct.pack("<d", half_slice)); f.write(struct.pack("<ii", pen, L["x"].size))
+        for a, dt in ((L["x"], np.uint16), (L["y"], np.uint16), (L["t"], np.int64), (L["p"], np.uint8)):
+            f.write(np.ascontiguousarray(a, dt).tobytes())
+        f.write(tl.tobytes()); f.write(tr.tobytes()); f.write(tl.tobytes())
+        f.write(struct.pack("<i", s["pose_t"].size)); f.write(np.ascontiguousarray(s["pose_t"], np.int64).tobytes())
+        f.write(np.ascontiguousarray(s["poses"], np.float64).tobytes())
+    p = subprocess.run([exe, str(scen), "8", str(frames)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = p.stdout.strip().splitlines()
+    world = int(lines[0].split()[1])
+    recs = np.array([[float(v) for v in ln.split()[1:]] for ln in lines[1:]])
+    assert recs.shape == (world, len(edist.RECORD_FIELDS)) and world >= 1
+    print("C++ multi-stream host:", world, "stream(s)")
+    st_ref = ind.sample_pose_stamps(s["t_ts_ns"], half_slice)
+    idx = np.searchsorted(s["pose_t"], st_ref, side="left"); keep = idx < s["pose_t"].size
+    for rank in range(world):
+        g = capi.Backend(product_lib, l, r, configs.params_for("hkust", product_lib))
+        sel = ind.select_close_events(L["t"], s["t_ts_ns"], half_slice, pen - 200 * rank)
+        g.set_ts_pair(tl, tr, Tw)
+        for _ in range(frames):
+            c = g.mapping_at_time(L["x"][sel], L["y"][sel], L["t"][sel], st_ref[keep], s["poses"][idx[keep]])
+        rec = edist.make_record(rank, frames, c, edist.map_checksum(g.map_download()))
+        g.close()
+        assert np.array_equal(recs[rank][:7], rec[:7]) and recs[rank][8] == rec[8], (rank, recs[rank], rec)
+        assert abs(recs[rank][7] - rec[7]) <= 0.01 * rec[7]                                  # lm_evals (nfev-style counter)
+        assert abs(recs[rank][9] - rec[9]) <= 1e-9 * abs(rec[9]), (rank, recs[rank][9], rec[9])
