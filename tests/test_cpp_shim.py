@@ -246,9 +246,9 @@ def test_multi_stream_nccl_gather_matches_python_records(oracle_lib, product_lib
         f.write(np.ascontiguousarray(s["poses"], np.float64).tobytes())
     p = subprocess.run([exe, str(scen), "8", str(frames)], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
-    lines = p.stdout.strip().splitlines()
-    world = int(lines[0].split()[1])
-    recs = np.array([[float(v) for v in ln.split()[1:]] for ln in lines[1:]])
+    lines = p.stdout.strip().splitlines()                      # NCCL may print its version banner on stdout first
+    world = int([ln for ln in lines if ln.startswith("streams ")][0].split()[1])
+    recs = np.array([[float(v) for v in ln.split()[1:]] for ln in lines if ln.startswith("record ")])
     assert recs.shape == (world, len(edist.RECORD_FIELDS)) and world >= 1
     print("C++ multi-stream host:", world, "stream(s)")
     st_ref = ind.sample_pose_stamps(s["t_ts_ns"], half_slice)
