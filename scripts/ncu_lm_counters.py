@@ -35,7 +35,7 @@ def counters(rep, kre):
 
 one, sat = counters(sys.argv[1], "lm2_kernel"), counters(sys.argv[2], "lm2_kernel")
 ev1, evs = float(sys.argv[3]), float(sys.argv[4])
-bm = counters(sys.argv[1], "bm_kernel")
+bm = counters(sys.argv[1], "bm_.*kernel")
 out = {
     "source": "ncu --set full --clock-control none on `bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-parity --no-extras` (one frame's launch, "
               "gpurun_out/prof_r2.ncu-rep) and on `scripts/lm_saturation.py --child 12011` (16 frames' seeds in one launch, gpurun_out/lm_sat_r2.ncu-rep); "
