@@ -44,6 +44,8 @@ struct MapState {
   int32_t* next = nullptr;       // per contribution (9 per staged point)
   int32_t* sort_pool = nullptr;  // ids of the long contribution lists, one segment per pixel (capacity = all contributions)
   int32_t* active = nullptr;     // pixels touched since the last reset, in first-touch order (count in d_scal[3])
+  int32_t* pcnt = nullptr;       // contributions staged per pixel since its list was last folded (zeroed by the fold)
+  int32_t* active_sorted = nullptr;  // the active pixels ordered by contribution count, longest first (fold_order_kernel)
   uint32_t* cbits = nullptr;     // one bit per contribution id: "this contribution created its pixel's element" (ordered hand-off)
   uint32_t* cprefix = nullptr;   // exclusive popcount prefix per word of cbits
   size_t cbits_words = 0;
@@ -80,7 +82,7 @@ struct FrameSet {
 };
 struct Pose16 { double m[16]; };
 __global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, Pose16 Tfw, int radius, int stage_off, PropSoA P, int32_t* head,
-                                  int32_t* next, int32_t* active, unsigned long long* scal) {
+                                  int32_t* next, int32_t* active, int32_t* pcnt, unsigned long long* scal) {
   const double* T_frame_world = Tfw.m;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= fs.off[fs.nframes]) return;
@@ -139,6 +141,7 @@ __global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, Pose16 Tfw, int rad
       const int pix = r * dc.W + c;
       const int old = atomicExch(&head[pix], cid);
       next[cid] = old;
+      atomicAdd(&pcnt[pix], 1);
       // first contribution to this pixel since its list was last folded: the pixel joins the active list (a pixel that
       // is folded twice between two resets is listed twice; the list kernels tolerate that, see map_*_list)
       if (old < 0) active[atomicAdd(&scal[3], 1ULL)] = pix;
@@ -147,7 +150,7 @@ __global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, Pose16 Tfw, int rad
 
 // ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
 // NAIVE = DepthFusion::naive_propagation (:232-288): same ordered replay, but nearest-wins instead of fusion.
-struct CleanArgs { int enable; double var_thr, age_thr, rmax, rmin; };
+struct CleanArgs { int enable; double var_thr, age_thr, rmax, rmin; int fast_div; };
 
 // ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
 // The state of one map pixel while its contribution list is replayed.
@@ -161,6 +164,7 @@ struct FoldState {
   // p_cam is overwritten by every create / fuse step and never read back by the recurrence, so it is evaluated once at the
   // end from the inverse depth that set it last (pc_rho); a replacement copies the propagated p_cam.
   bool pc_pending;
+  bool fast;           // branch-free division / square root in the Student-t update (ESVO_FOLD_FASTDIV, default on)
   double pc_rho;
   double sdm;          // 2*sqrt(var) of the map point, refreshed whenever var changes
 };
@@ -212,6 +216,7 @@ __device__ __forceinline__ void fold_apply(const DevConsts& dc, const PropSoA& P
     compat = diff < r.sd2 || diff < f.sdm;
   }
   if (compat) {  // case 2.1 (:162-177)
+    bool fast_sqrt = false;
     if (!(f.rho > -1e-6)) {
       // DepthPoint::update / update_studentT take their "new point" branch for a map point that carries no valid inverse
       // depth (DepthPoint.cpp:158-163,181-187): overwrite, no inner age_++
@@ -225,14 +230,28 @@ __device__ __forceinline__ void fold_apply(const DevConsts& dc, const PropSoA& P
       if (f.var < 1e-6) f.var = 1e-6;
     } else {
       const double nu_u = fmin(pnu, f.nu);
-      const double rho_u = (ps2 * f.rho + f.s2 * prho) / (f.s2 + ps2);
+      const double S = f.s2 + ps2;
       const double dd = f.rho - prho;
-      const double s2_u = (nu_u + (dd * dd) / (f.s2 + ps2)) / (nu_u + 1) * (f.s2 * ps2) / (f.s2 + ps2);
-      f.rho = rho_u; f.s2 = s2_u; f.nu = nu_u + 1;
-      f.var = f.nu / (f.nu - 2) * f.s2;
-      f.age++;                                   // DepthPoint.cpp:179
+      if (f.fast && S > 1e-200 && S < 1e200 && nu_u > 2.0 && nu_u < 1e15) {
+        // the three divisions by S share one reciprocal; every quotient gets its own remainder correction (Markstein), i.e.
+        // the correctly rounded value except for rare 1-ulp cases -- same arithmetic, a third of the dependent latency
+        const double xr = rcp_nr(S);
+        auto divS = [&](double a) { const double q = a * xr; return fma(fma(-S, q, a), xr, q); };
+        const double rho_u = divS(ps2 * f.rho + f.s2 * prho);
+        const double s2_u = divS(div_nr(nu_u + divS(dd * dd), nu_u + 1) * (f.s2 * ps2));
+        f.rho = rho_u; f.s2 = s2_u; f.nu = nu_u + 1;
+        f.var = div_nr(f.nu, f.nu - 2) * f.s2;
+        f.age++;
+        fast_sqrt = f.var > 1e-200 && f.var < 1e200;
+      } else {
+        const double rho_u = (ps2 * f.rho + f.s2 * prho) / S;
+        const double s2_u = (nu_u + (dd * dd) / S) / (nu_u + 1) * (f.s2 * ps2) / S;
+        f.rho = rho_u; f.s2 = s2_u; f.nu = nu_u + 1;
+        f.var = f.nu / (f.nu - 2) * f.s2;
+        f.age++;                                   // DepthPoint.cpp:179
+      }
     }
-    f.sdm = 2 * sqrt(f.var);
+    f.sdm = fast_sqrt ? 2 * sqrt_nr(f.var) : 2 * sqrt(f.var);
     f.age++;                                     // DepthFusion.cpp:171
     f.res = fmin(f.res, pres);
     f.pc_rho = prho; f.pc_pending = true;        // p_cam from the PROPAGATED rho (:174)
@@ -280,9 +299,34 @@ __device__ __forceinline__ void heap_sort_i32(int* ids, int cnt) {
   for (int st = (cnt - 2) / 2; st >= 0; --st) sift(st, cnt - 1);
   for (int end = cnt - 1; end > 0; --end) { int tmp = ids[end]; ids[end] = ids[0]; ids[0] = tmp; sift(0, end - 1); }
 }
+// Counting sort of the active pixels by their number of staged contributions, longest first (one block; a few thousand
+// pixels).  A fold warp lives as long as the longest list among its 32 pixels: in first-touch order the sum of the per-warp
+// maxima is 2.5x the sum in sorted order (13 140 vs 5 320 replay steps on the bench frame, ideal 5 230), and that warp-slot
+// time is what the fold costs the frame pipeline.  Launching the longest lists first also shortens the kernel's tail.
+__global__ void __launch_bounds__(1024) fold_order_kernel(const int32_t* __restrict__ active, const int32_t* __restrict__ pcnt,
+                                                          const unsigned long long* __restrict__ scal, int32_t* __restrict__ sorted) {
+  __shared__ int s_hist[256], s_base[256];
+  const int n = (int)scal[3];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_hist[min(pcnt[active[i]], 255)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) { int run = 0; for (int b = 255; b >= 0; --b) { s_base[b] = run; run += s_hist[b]; } }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int pix = active[i];
+    sorted[atomicAdd(&s_base[min(pcnt[pix], 255)], 1)] = pix;
+  }
+}
+// ids of one pixel's contributions -> sequence order.  (The walk order is NOT close to sorted: an "reverse + insertion sort"
+// variant lost 13 % of step time to the heap sort, profiles/r2_sweeps.md.)
+__device__ __forceinline__ void sort_ids(int* ids, int cnt) {
+  if (cnt <= 16) { for (int a = 1; a < cnt; ++a) { int v = ids[a], b = a - 1; while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; } ids[b + 1] = v; } }
+  else heap_sort_i32(ids, cnt);   // O(L log L) on the local array
+}
 template <bool NAIVE>
 __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* head, const int32_t* __restrict__ next,
-                                 const int32_t* __restrict__ active, unsigned long long seq_base, unsigned long long* scal,
+                                 const int32_t* __restrict__ active, int32_t* pcnt, unsigned long long seq_base, unsigned long long* scal,
                                  uint32_t* cbits, CleanArgs clean, int32_t* sort_pool) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if ((unsigned long long)t >= scal[3]) return;
@@ -290,6 +334,7 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
   int h = head[pix];
   if (h < 0) return;               // listed twice: the first copy folded it
   head[pix] = -1;
+  pcnt[pix] = 0;
   // The list is in reverse insertion order of the atomics, not in sequence order: collect and sort.
   constexpr int CAP = 192;
   int ids[CAP];
@@ -298,10 +343,9 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
   const int row = pix / dc.W, col = pix - row * dc.W;
   FoldState f;
   fold_load(M, pix, row, col, f);
+  f.fast = clean.fast_div != 0;
   if (total <= CAP) {
-    if (cnt <= 16) {
-      for (int a = 1; a < cnt; ++a) { int v = ids[a], b = a - 1; while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; } ids[b + 1] = v; }
-    } else heap_sort_i32(ids, cnt);   // O(L log L) on the local array
+    sort_ids(ids, cnt);
     FoldRec cur = P.hot[ids[0] / 9];
     for (int a = 0; a < cnt; ++a) {              // the next record is in flight while this one is folded
       FoldRec nxt = cur;
@@ -315,7 +359,7 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
     int* seg = sort_pool + atomicAdd(&scal[5], (unsigned long long)total);
     int k = 0;
     for (int q = h; q >= 0; q = next[q]) seg[k++] = q;
-    heap_sort_i32(seg, total);
+    sort_ids(seg, total);
     FoldRec cur = P.hot[seg[0] / 9];
     for (int a = 0; a < total; ++a) {
       FoldRec nxt = cur;
@@ -338,7 +382,7 @@ constexpr int FOLD_CAPW = 256;        // ids per pixel held in shared memory; lo
 // blocks wait for several neighbouring LM warps to retire (measured: 0.27 -> 0.32 ms/step with 4-warp blocks).
 template <bool NAIVE, int FOLD_WPB>
 __global__ void __launch_bounds__(FOLD_WPB * 32, 16 / FOLD_WPB) fuse_fold_warp_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* head,
-                                                                        const int32_t* __restrict__ next, const int32_t* __restrict__ active,
+                                                                        const int32_t* __restrict__ next, const int32_t* __restrict__ active, int32_t* pcnt,
                                                                         unsigned long long seq_base, unsigned long long* scal, uint32_t* cbits,
                                                                         CleanArgs clean) {
   __shared__ int s_ids[FOLD_WPB][FOLD_CAPW], s_sorted[FOLD_WPB][FOLD_CAPW];
@@ -353,6 +397,7 @@ __global__ void __launch_bounds__(FOLD_WPB * 32, 16 / FOLD_WPB) fuse_fold_warp_k
       h = head[pix];
       if (h >= 0) {
         head[pix] = -1;
+        pcnt[pix] = 0;
         for (int q = h; q >= 0; q = next[q]) { if (total < FOLD_CAPW) s_ids[w][total] = q; ++total; }   // serial list walk
       }
     }
@@ -362,6 +407,7 @@ __global__ void __launch_bounds__(FOLD_WPB * 32, 16 / FOLD_WPB) fuse_fold_warp_k
     const int row = pix / dc.W, col = pix - row * dc.W;
     FoldState f;
     fold_load(M, pix, row, col, f);
+    f.fast = clean.fast_div != 0;
     if (total <= FOLD_CAPW) {
       // rank sort: ids are distinct, rank = number of smaller ids
       for (int e = lane; e < total; e += 32) {
@@ -832,6 +878,8 @@ int fuse_alloc(Ctx* c) {
   ESVO_CUDA_TRY(c, dm(&M.first_key, npix));
   ESVO_CUDA_TRY(c, dm(&ms->head, npix));
   ESVO_CUDA_TRY(c, dm(&ms->active, npix));
+  ESVO_CUDA_TRY(c, dm(&ms->pcnt, npix)); ESVO_CUDA_TRY(c, dm(&ms->active_sorted, npix));
+  ESVO_CUDA_TRY(c, cudaMemset(ms->pcnt, 0, npix * 4));       // invariant: every fold zeroes the counts it consumed
   ESVO_CUDA_TRY(c, dm(&ms->d_dl, npix)); ESVO_CUDA_TRY(c, dm(&ms->d_dl_keys, npix));
   ESVO_CUDA_TRY(c, dm(&ms->d_scal, 8));
   ESVO_CUDA_TRY(c, cudaMallocHost((void**)&ms->h_scal, 4 * 8));
@@ -848,7 +896,7 @@ void fuse_free(Ctx* c) {
   MapSoA& M = ms->m; PropSoA& P = ms->p;
   void* ps[] = {M.exists, M.rho, M.s2, M.nu, M.var, M.res, M.x0, M.x1, M.pc0, M.pc1, M.pc2, M.rho_tmp, M.age, M.row, M.col,
                 M.first_key, P.hot, P.ok, P.rho, P.s2, P.nu, P.var, P.res, P.x0, P.x1, P.pc0, P.pc1, P.pc2, P.age, P.row, P.col,
-                ms->head, ms->next, ms->active, ms->cbits, ms->cprefix, ms->sort_pool, ms->d_dl, ms->d_dl_keys, ms->d_scal};
+                ms->head, ms->next, ms->active, ms->pcnt, ms->active_sorted, ms->cbits, ms->cprefix, ms->sort_pool, ms->d_dl, ms->d_dl_keys, ms->d_scal};
   for (void* p : ps) if (p) cudaFree(p);
   if (ms->h_scal) cudaFreeHost(ms->h_scal);
   delete ms;
@@ -904,7 +952,7 @@ int fuse_points(Ctx* c, const esvo_depth_point* d_pts, size_t n_cap, const uint6
   if (naive) dcs.lsnorm = ESVO_LSNORM_L2;
   Pose16 Tfw; std::memcpy(Tfw.m, ms->T_frame_world, 128);
   fuse_stage_kernel<<<div_up((int)n_cap, B), B, 0, c->stream>>>(dcs, fs, Tfw, radius, (int)ms->staged, ms->p, ms->head, ms->next,
-                                                                ms->active, ms->d_scal);
+                                                                ms->active, ms->pcnt, ms->d_scal);
   c->launches += 1;
   ms->staged += n_cap;
   ESVO_CUDA_TRY(c, cudaGetLastError());
@@ -930,7 +978,7 @@ int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
     if (tot == 0) continue;
     if (ms->staged + (size_t)tot > ms->prop_cap) { c->set_error("fusion staging capacity exceeded"); return ESVO_ERR_CAPACITY; }
     fuse_stage_kernel<<<div_up(tot, B), B, 0, c->stream>>>(c->dc, fs, Tfw, radius, (int)ms->staged, ms->p, ms->head, ms->next, ms->active,
-                                                           ms->d_scal);
+                                                           ms->pcnt, ms->d_scal);
     c->launches += 1;
     ms->staged += (size_t)tot;
   }
@@ -943,7 +991,9 @@ int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
 int fuse_finish(Ctx* c, bool naive, const double* clean4) {
   MapState* ms = c->map;
   if (ms->staged == 0) return ESVO_OK;
-  CleanArgs ca{0, 0, 0, 0, 0};
+  CleanArgs ca{0, 0, 0, 0, 0, 0};
+  static const int fast_div = getenv("ESVO_FOLD_FASTDIV") ? atoi(getenv("ESVO_FOLD_FASTDIV")) : 1;
+  ca.fast_div = fast_div;
   if (clean4) { ca.enable = 1; ca.var_thr = clean4[0]; ca.age_thr = clean4[1]; ca.rmax = clean4[2]; ca.rmin = clean4[3]; }
   // creator bits feed the sort-free ordered hand-off; only meaningful for the first fold after a reset
   uint32_t* cbits = nullptr;
@@ -960,17 +1010,25 @@ int fuse_finish(Ctx* c, bool naive, const double* clean4) {
   if (!warp_fold) {
     const int npix = c->dc.W * c->dc.H, B = 32;
     const int bound = (int)std::min<size_t>((size_t)npix, ms->staged * 9);
-    if (naive) fuse_fold_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool);
-    else fuse_fold_kernel<false><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool);
+    // pixels ordered by list length, longest first (ESVO_FOLD_SORT=0: first-touch order)
+    static const int sort_lists = getenv("ESVO_FOLD_SORT") ? atoi(getenv("ESVO_FOLD_SORT")) : 1;
+    const int32_t* order = ms->active;
+    if (sort_lists) {
+      fold_order_kernel<<<1, 1024, 0, c->stream>>>(ms->active, ms->pcnt, ms->d_scal, ms->active_sorted);
+      c->launches += 1;
+      order = ms->active_sorted;
+    }
+    if (naive) fuse_fold_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, order, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool);
+    else fuse_fold_kernel<false><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, order, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool);
   } else {   // persistent: one-warp blocks walk the active list, one warp per pixel
     static const int G = getenv("ESVO_DBG_FOLD_GRID") ? atoi(getenv("ESVO_DBG_FOLD_GRID")) : 148 * 16;
     static const int wpb = getenv("ESVO_DBG_FOLD_WPB") ? atoi(getenv("ESVO_DBG_FOLD_WPB")) : 1;
     if (wpb == 4) {
-      if (naive) fuse_fold_warp_kernel<true, 4><<<G, 128, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
-      else fuse_fold_warp_kernel<false, 4><<<G, 128, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+      if (naive) fuse_fold_warp_kernel<true, 4><<<G, 128, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca);
+      else fuse_fold_warp_kernel<false, 4><<<G, 128, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca);
     } else {
-      if (naive) fuse_fold_warp_kernel<true, 1><<<G, 32, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
-      else fuse_fold_warp_kernel<false, 1><<<G, 32, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->seq_base, ms->d_scal, cbits, ca);
+      if (naive) fuse_fold_warp_kernel<true, 1><<<G, 32, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca);
+      else fuse_fold_warp_kernel<false, 1><<<G, 32, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, ms->active, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca);
     }
   }
   c->launches += 1;
