@@ -150,7 +150,7 @@ __global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, Pose16 Tfw, int rad
 
 // ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
 // NAIVE = DepthFusion::naive_propagation (:232-288): same ordered replay, but nearest-wins instead of fusion.
-struct CleanArgs { int enable; double var_thr, age_thr, rmax, rmin; int fast_div; };
+struct CleanArgs { int enable; double var_thr, age_thr, rmax, rmin; int fast_div, net_sort; };
 
 // ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
 // The state of one map pixel while its contribution list is replayed.
@@ -320,8 +320,34 @@ __global__ void __launch_bounds__(1024) fold_order_kernel(const int32_t* __restr
 }
 // ids of one pixel's contributions -> sequence order.  (The walk order is NOT close to sorted: an "reverse + insertion sort"
 // variant lost 13 % of step time to the heap sort, profiles/r2_sweeps.md.)
-__device__ __forceinline__ void sort_ids(int* ids, int cnt) {
-  if (cnt <= 16) { for (int a = 1; a < cnt; ++a) { int v = ids[a], b = a - 1; while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; } ids[b + 1] = v; } }
+// Lists of up to 64 ids go through a bitonic NETWORK held in registers (compile-time indices: 240 / 672 compare-exchanges of
+// two instructions each, no memory traffic, no data-dependent branches); the local array is only the hand-over format of the
+// list walk before and of the replay after.  Longer lists keep the heap sort.
+template <int N>
+__device__ __forceinline__ void network_sort_local(int* ids, int cnt) {
+  int v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = i < cnt ? ids[i] : 0x7fffffff;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1)
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const int a = v[i], b = v[l];
+          const int lo = min(a, b), hi = max(a, b);
+          if ((i & k) == 0) { v[i] = lo; v[l] = hi; } else { v[i] = hi; v[l] = lo; }
+        }
+      }
+#pragma unroll
+  for (int i = 0; i < N; ++i) if (i < cnt) ids[i] = v[i];
+}
+__device__ __forceinline__ void sort_ids(int* ids, int cnt, bool network) {
+  if (cnt <= 16 && !network) { for (int a = 1; a < cnt; ++a) { int v = ids[a], b = a - 1; while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; } ids[b + 1] = v; } }
+  else if (network && cnt <= 32) network_sort_local<32>(ids, cnt);
+  else if (network && cnt <= 64) network_sort_local<64>(ids, cnt);
   else heap_sort_i32(ids, cnt);   // O(L log L) on the local array
 }
 template <bool NAIVE>
@@ -345,7 +371,7 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
   fold_load(M, pix, row, col, f);
   f.fast = clean.fast_div != 0;
   if (total <= CAP) {
-    sort_ids(ids, cnt);
+    sort_ids(ids, cnt, clean.net_sort != 0);
     FoldRec cur = P.hot[ids[0] / 9];
     for (int a = 0; a < cnt; ++a) {              // the next record is in flight while this one is folded
       FoldRec nxt = cur;
@@ -359,7 +385,7 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
     int* seg = sort_pool + atomicAdd(&scal[5], (unsigned long long)total);
     int k = 0;
     for (int q = h; q >= 0; q = next[q]) seg[k++] = q;
-    sort_ids(seg, total);
+    sort_ids(seg, total, false);
     FoldRec cur = P.hot[seg[0] / 9];
     for (int a = 0; a < total; ++a) {
       FoldRec nxt = cur;
@@ -991,7 +1017,9 @@ int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
 int fuse_finish(Ctx* c, bool naive, const double* clean4) {
   MapState* ms = c->map;
   if (ms->staged == 0) return ESVO_OK;
-  CleanArgs ca{0, 0, 0, 0, 0, 0};
+  CleanArgs ca{0, 0, 0, 0, 0, 0, 0};
+  static const int net_sort = getenv("ESVO_FOLD_NETSORT") ? atoi(getenv("ESVO_FOLD_NETSORT")) : 1;
+  ca.net_sort = net_sort;
   static const int fast_div = getenv("ESVO_FOLD_FASTDIV") ? atoi(getenv("ESVO_FOLD_FASTDIV")) : 1;
   ca.fast_div = fast_div;
   if (clean4) { ca.enable = 1; ca.var_thr = clean4[0]; ca.age_thr = clean4[1]; ca.rmax = clean4[2]; ca.rmin = clean4[3]; }
