@@ -745,8 +745,44 @@ def run_ours(args, rank, world, local_rank):
             extras["cfg3"] = run_cfg3(args, prod, local_rank)
         except Exception as ex:       # an extra must never take the headline line down
             extras["cfg3"] = {"error": repr(ex)}
+        try:
+            extras["sgm_init"] = sgm_block(prod, base, cfg["rig"], local_rank)
+        except Exception as ex:
+            extras["sgm_init"] = {"error": repr(ex)}
     out["extras"] = extras
     print(json.dumps(out))
+
+
+def sgm_block(prod, base, rig, local_rank):
+    """The one-off initialisation of the mapper (esvo_Mapping::InitializationAtTime, esvo_Mapping.cpp:433-492): cv::StereoSGBM
+    (0, 48, 11, 968, 3872, -1, 0, 11) on the time-surface pair on the device (esvo_sgbm_compute, bit-exact vs cv2: tests/test_gpu_sgbm.py)
+    followed by esvo_init_from_disparity; host wall clock around the synchronous C-ABI calls, cv2 on the host cores beside it."""
+    from esvo_b200 import capi, configs
+    l, r = configs.rig_calibs(rig)
+    g = capi.Backend(prod, l, r, configs.params_for(rig, prod), device=local_rank)
+    for cam, side in ((0, "left"), (1, "right")):
+        e = base[side]
+        g.ts_push_events(cam, e["x"], e["y"], e["t"], e["p"])
+    _, tl = g.ts_build(0, base["t_ts_ns"], want_idx=False); _, tr = g.ts_build(1, base["t_ts_ns"], want_idx=False)
+    g.set_ts_pair(None, None, base["T_world_left"])
+    ts = []
+    for _ in range(4):
+        t0 = time.perf_counter(); d = g.sgbm_compute(); ts.append((time.perf_counter() - t0) * 1e3)
+    sd = base["seeds"]
+    t0 = time.perf_counter(); n_pts, acc = g.init_from_disparity(d, sd["x"], sd["y"], base["T_world_left"], 1); t_init = (time.perf_counter() - t0) * 1e3
+    out = {"sgbm_ms": float(np.median(ts[1:])), "init_from_disparity_ms": t_init, "sgm_points": int(n_pts), "accepted": bool(acc),
+           "valid_disparities": int((d >= 0).sum()), "note": "one-off at start-up; host wall clock around synchronous calls incl. the D2H of the disparity map"}
+    g.close()
+    try:
+        import cv2
+        m = cv2.StereoSGBM_create(0, 48, 11, 8 * 121, 32 * 121, -1, 0, 11)
+        tc = []
+        for _ in range(3):
+            t0 = time.perf_counter(); ref = m.compute(tl, tr); tc.append((time.perf_counter() - t0) * 1e3)
+        out["cv2_sgbm_ms"] = float(np.median(tc)); out["bit_exact_vs_cv2"] = bool(np.array_equal(ref, d))
+    except ImportError:
+        pass
+    return out
 
 
 def run_cfg3(args, prod, local_rank):
