@@ -194,7 +194,17 @@ class StreamDriver:
     def to_pinned(f):
         import torch
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-        d = {side: {k: pin(v) for k, v in f[side].items()} for side in ("left", "right")}
+
+        def packet(e):
+            """One pinned packet buffer per camera and frame, laid out t | x | y | p like a driver's SoA event packet: the library
+            moves arrays that are adjacent in host memory with a single copy (esvo_stage_ts_events)."""
+            n = e["x"].size
+            buf = torch.zeros(13 * n, dtype=torch.uint8).pin_memory().numpy()
+            out = {"t": buf[:8 * n].view(np.int64), "x": buf[8 * n:10 * n].view(np.uint16), "y": buf[10 * n:12 * n].view(np.uint16), "p": buf[12 * n:13 * n]}
+            for k in out:
+                out[k][:] = e[k]
+            return out
+        d = {side: packet(f[side]) for side in ("left", "right")}
         d["seeds"] = {k: pin(v) for k, v in f["seeds"].items()}
         d["pose_t"] = pin(f["pose_t"]); d["poses"] = pin(f["poses"])
         d["t_ts_ns"] = int(f["t_ts_ns"]); d["T"] = np.ascontiguousarray(f["T_world_left"], np.float64)

@@ -150,7 +150,7 @@ __global__ void fuse_stage_kernel(DevConsts dc, FrameSet fs, Pose16 Tfw, int rad
 
 // ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
 // NAIVE = DepthFusion::naive_propagation (:232-288): same ordered replay, but nearest-wins instead of fusion.
-struct CleanArgs { int enable; double var_thr, age_thr, rmax, rmin; int fast_div, net_sort; };
+struct CleanArgs { int enable; double var_thr, age_thr, rmax, rmin; int fast_div, net_sort, dbg_phase; };   // dbg_phase: timing probe (scripts/fold_probe.py), 0 = off
 
 // ---- fold: DepthFusion::fusion (:123-190) replayed per pixel in sequence order ----
 // The state of one map pixel while its contribution list is replayed.
@@ -303,15 +303,19 @@ __device__ __forceinline__ void heap_sort_i32(int* ids, int cnt) {
 // pixels).  A fold warp lives as long as the longest list among its 32 pixels: in first-touch order the sum of the per-warp
 // maxima is 2.5x the sum in sorted order (13 140 vs 5 320 replay steps on the bench frame, ideal 5 230), and that warp-slot
 // time is what the fold costs the frame pipeline.  Launching the longest lists first also shortens the kernel's tail.
+constexpr int FOLD_LONG = 64;        // lists longer than this are folded by a whole warp (fuse_fold_hybrid_kernel)
 __global__ void __launch_bounds__(1024) fold_order_kernel(const int32_t* __restrict__ active, const int32_t* __restrict__ pcnt,
-                                                          const unsigned long long* __restrict__ scal, int32_t* __restrict__ sorted) {
+                                                          unsigned long long* __restrict__ scal, int32_t* __restrict__ sorted) {
   __shared__ int s_hist[256], s_base[256];
   const int n = (int)scal[3];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_hist[min(pcnt[active[i]], 255)], 1);
   __syncthreads();
-  if (threadIdx.x == 0) { int run = 0; for (int b = 255; b >= 0; --b) { s_base[b] = run; run += s_hist[b]; } }
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = 255; b >= 0; --b) { s_base[b] = run; run += s_hist[b]; if (b == FOLD_LONG + 1) scal[6] = (unsigned long long)run; }   // lists longer than FOLD_LONG
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int pix = active[i];
@@ -367,11 +371,13 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
   int cnt = 0, total = 0;
   for (int q = h; q >= 0; q = next[q]) { if (cnt < CAP) ids[cnt++] = q; ++total; }
   const int row = pix / dc.W, col = pix - row * dc.W;
+  if (clean.dbg_phase == 1) { if (total == 0x7fffffff) M.rho[pix] = ids[0]; return; }          // probe: list walk only
   FoldState f;
   fold_load(M, pix, row, col, f);
   f.fast = clean.fast_div != 0;
   if (total <= CAP) {
     sort_ids(ids, cnt, clean.net_sort != 0);
+    if (clean.dbg_phase == 2) { if (ids[cnt - 1] == 0x7fffffff) M.rho[pix] = ids[0]; return; }  // probe: walk + sort
     FoldRec cur = P.hot[ids[0] / 9];
     for (int a = 0; a < cnt; ++a) {              // the next record is in flight while this one is folded
       FoldRec nxt = cur;
@@ -395,6 +401,126 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
     }
   }
   fold_store(dc, M, pix, f, clean, cbits, seq_base, scal);
+}
+
+// Hybrid form (ESVO_FOLD_HYBRID=1, latency-critical use; NOT the default): the length-sorted active list starts with the long lists (> FOLD_LONG contributions, scal[6] of
+// them).  Those go one per WARP to the first G_long blocks: lane 0 walks the list into shared memory, the 32 lanes sort it
+// there with a bitonic network, fetch the 48-byte records 32 at a time and broadcast them step by step to a replay that runs
+// redundantly in every lane (uniform control flow; lane 0 stores).  Measured alone (scripts/fold_probe.py): a thread's heap
+// sort of a 160-id list in local memory costs more than its replay, and in the 640x480 rig (fusion radius 1: lists of several
+// hundred ids, heap-sorted in the global pool) the long lists are 85 % of the fusion stage.  All other blocks fold 32 short
+// lists each, one per thread, with the register sorting network.  Alone the fusion stage drops from 0.33 to 0.19 ms (346x260)
+// and 1.73 to 1.61 ms (640x480) -- but in the frame pipeline a warp that replays ONE list in 32 redundant lanes spends 32x the
+// issue slots of a lane that replays it next to 31 other lists: 0.217 -> 0.228 ms/step.  Throughput wants the thread form.
+constexpr int FOLD_CAPL = 1024;      // ids of a long list held in shared memory; beyond that lane 0 falls back to the pool heap sort
+template <bool NAIVE>
+__global__ void __launch_bounds__(32, 16) fuse_fold_hybrid_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* head, const int32_t* __restrict__ next,
+                                                              const int32_t* __restrict__ sorted, int32_t* pcnt, unsigned long long seq_base,
+                                                              unsigned long long* scal, uint32_t* cbits, CleanArgs clean, int32_t* sort_pool,
+                                                              int G_long) {
+  __shared__ int s_ids[FOLD_CAPL];
+  const unsigned FULLM = 0xffffffffu;
+  const int lane = threadIdx.x;
+  const int n_active = (int)scal[3], n_long = min((int)scal[6], n_active);
+  if ((int)blockIdx.x >= G_long) {
+    // ---------------- short lists: one per thread ----------------
+    const int t = n_long + ((int)blockIdx.x - G_long) * 32 + lane;
+    if (t >= n_active) return;
+    const int pix = sorted[t];
+    const int h = head[pix];
+    if (h < 0) return;               // listed twice: the first copy folded it
+    head[pix] = -1;
+    pcnt[pix] = 0;
+    constexpr int CAP = 192;
+    int ids[CAP];
+    int cnt = 0, total = 0;
+    for (int q = h; q >= 0; q = next[q]) { if (cnt < CAP) ids[cnt++] = q; ++total; }
+    const int row = pix / dc.W, col = pix - row * dc.W;
+    FoldState f;
+    fold_load(M, pix, row, col, f);
+    f.fast = clean.fast_div != 0;
+    int* seq = ids;
+    if (total > CAP) {               // cannot happen while pcnt is exact; kept as the general fallback
+      seq = sort_pool + atomicAdd(&scal[5], (unsigned long long)total);
+      int k = 0;
+      for (int q = h; q >= 0; q = next[q]) seq[k++] = q;
+      sort_ids(seq, total, false);
+    } else sort_ids(ids, cnt, true);
+    FoldRec cur = P.hot[seq[0] / 9];
+    for (int a = 0; a < total; ++a) {              // the next record is in flight while this one is folded
+      FoldRec nxt = cur;
+      if (a + 1 < total) nxt = P.hot[seq[a + 1] / 9];
+      fold_apply<NAIVE>(dc, P, f, row, col, seq[a], cur, seq_base);
+      cur = nxt;
+    }
+    fold_store(dc, M, pix, f, clean, cbits, seq_base, scal);
+    return;
+  }
+  // ---------------- long lists: one per warp ----------------
+  for (int t = blockIdx.x; t < n_long; t += G_long) {
+    const int pix = sorted[t];
+    int h = 0, total = 0;
+    int* seq = s_ids;
+    if (lane == 0) {
+      h = head[pix];
+      if (h >= 0) {
+        head[pix] = -1;
+        pcnt[pix] = 0;
+        for (int q = h; q >= 0; q = next[q]) { if (total < FOLD_CAPL) s_ids[total] = q; ++total; }   // serial list walk
+      }
+    }
+    h = __shfl_sync(FULLM, h, 0); total = __shfl_sync(FULLM, total, 0);
+    if (h < 0) continue;
+    if (total > FOLD_CAPL) {         // very long list: pool segment, heap-sorted by lane 0
+      unsigned long long base = 0;
+      if (lane == 0) {
+        base = atomicAdd(&scal[5], (unsigned long long)total);
+        int* seg = sort_pool + base;
+        int k = 0;
+        for (int q = h; q >= 0; q = next[q]) seg[k++] = q;
+        heap_sort_i32(seg, total);
+        __threadfence_block();
+      }
+      base = __shfl_sync(FULLM, base, 0);
+      seq = sort_pool + base;
+    } else {
+      int N = 64;
+      while (N < total) N <<= 1;
+      for (int i = total + lane; i < N; i += 32) s_ids[i] = 0x7fffffff;
+      __syncwarp();
+      for (int k = 2; k <= N; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < N; i += 32) {
+            const int l = i ^ j;
+            if (l > i) {
+              const int a = s_ids[i], b = s_ids[l];
+              if ((a > b) == ((i & k) == 0)) { s_ids[i] = b; s_ids[l] = a; }
+            }
+          }
+          __syncwarp();
+        }
+    }
+    __syncwarp();
+    const int row = pix / dc.W, col = pix - row * dc.W;
+    FoldState f;
+    fold_load(M, pix, row, col, f);
+    f.fast = clean.fast_div != 0;
+    FoldRec mine;                    // record of step base + lane, fetched one chunk ahead
+    { const int e = lane < total ? lane : 0; mine = P.hot[seq[e] / 9]; }
+    for (int base = 0; base < total; base += 32) {
+      const FoldRec cur = mine;
+      if (base + 32 < total) { const int e = base + 32 + lane < total ? base + 32 + lane : base + 32; mine = P.hot[seq[e] / 9]; }
+      const int nstep = min(32, total - base);
+      for (int k = 0; k < nstep; ++k) {
+        FoldRec r;
+        r.rho = __shfl_sync(FULLM, cur.rho, k); r.s2 = __shfl_sync(FULLM, cur.s2, k); r.nu = __shfl_sync(FULLM, cur.nu, k);
+        r.var = __shfl_sync(FULLM, cur.var, k); r.res = __shfl_sync(FULLM, cur.res, k); r.sd2 = __shfl_sync(FULLM, cur.sd2, k);
+        fold_apply<NAIVE>(dc, P, f, row, col, seq[base + k], r, seq_base);
+      }
+    }
+    if (lane == 0) fold_store(dc, M, pix, f, clean, cbits, seq_base, scal);
+    __syncwarp();
+  }
 }
 
 // Warp-per-active-pixel form (ESVO_FOLD_WARP=1): lower latency alone, more warp-slot time in the pipeline.  A pixel's replay is inherently serial (every step depends on the state the previous one
@@ -1017,7 +1143,9 @@ int fuse_window(Ctx* c, const Ctx::WinFrame* frames, int nframes, int radius) {
 int fuse_finish(Ctx* c, bool naive, const double* clean4) {
   MapState* ms = c->map;
   if (ms->staged == 0) return ESVO_OK;
-  CleanArgs ca{0, 0, 0, 0, 0, 0, 0};
+  CleanArgs ca{0, 0, 0, 0, 0, 0, 0, 0};
+  static const int dbg_phase = getenv("ESVO_DBG_FOLD_PHASE") ? atoi(getenv("ESVO_DBG_FOLD_PHASE")) : 0;
+  ca.dbg_phase = dbg_phase;
   static const int net_sort = getenv("ESVO_FOLD_NETSORT") ? atoi(getenv("ESVO_FOLD_NETSORT")) : 1;
   ca.net_sort = net_sort;
   static const int fast_div = getenv("ESVO_FOLD_FASTDIV") ? atoi(getenv("ESVO_FOLD_FASTDIV")) : 1;
@@ -1046,7 +1174,12 @@ int fuse_finish(Ctx* c, bool naive, const double* clean4) {
       c->launches += 1;
       order = ms->active_sorted;
     }
-    if (naive) fuse_fold_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, order, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool);
+    static const int hybrid = getenv("ESVO_FOLD_HYBRID") ? atoi(getenv("ESVO_FOLD_HYBRID")) : 0;
+    if (sort_lists && hybrid && !ca.dbg_phase) {
+      const int G_long = 148 * 4;     // warps that walk the long lists; the other blocks take 32 short lists each
+      if (naive) fuse_fold_hybrid_kernel<true><<<G_long + div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, order, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool, G_long);
+      else fuse_fold_hybrid_kernel<false><<<G_long + div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, order, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool, G_long);
+    } else if (naive) fuse_fold_kernel<true><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, order, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool);
     else fuse_fold_kernel<false><<<div_up(bound, B), B, 0, c->stream>>>(c->dc, ms->m, ms->p, ms->head, ms->next, order, ms->pcnt, ms->seq_base, ms->d_scal, cbits, ca, ms->sort_pool);
   } else {   // persistent: one-warp blocks walk the active list, one warp per pixel
     static const int G = getenv("ESVO_DBG_FOLD_GRID") ? atoi(getenv("ESVO_DBG_FOLD_GRID")) : 148 * 16;

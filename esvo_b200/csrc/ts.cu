@@ -408,7 +408,7 @@ void ts_free(Ctx* c, int cam) {
   TsState& s = c->ts[cam];
   void* ps[] = {s.ex2, s.ey2, s.et2, s.ep2, s.ex, s.ey, s.et, s.ep, s.cur_idx, s.cur_t, s.cur_pol, s.base_idx, s.base_t, s.base_pol, s.tmp_idx,
                 s.tmp_t, s.tmp_pol, s.cnt, s.out_idx, s.img_med, s.img_out, s.map1, s.map2, s.scalars, s.max_t,
-                s.fwd_lut, s.fwd_head, s.fwd_next, s.fwd_val, s.raw_x, s.raw_y, s.raw_t, s.raw_p, s.raw_eff, s.agg, s.back};
+                s.fwd_lut, s.fwd_head, s.fwd_next, s.fwd_val, s.raw_x, s.raw_y, s.raw_t, s.raw_p, s.raw_eff, s.agg, s.back, s.pack_dev};
   for (void* p : ps) if (p) cudaFree(p);
   s = TsState();
 }
@@ -440,8 +440,21 @@ static int ts_make_room(Ctx* c, int cam, size_t n_new) {
 
 // x/y/t/p are HOST pointers; the copies are enqueued on the ctx stream (pageable memory is staged
 // by the driver; callers that want true async overlap pass pinned buffers).
+// Host event packet whose four arrays are adjacent (at most 64 bytes of padding in total): start of the span, else null.
+static const uint8_t* packet_span(const uint16_t* x, const uint16_t* y, const int64_t* t, const uint8_t* p, size_t n, size_t& span) {
+  static const int enabled = getenv("ESVO_TS_PACKET_COPY") ? atoi(getenv("ESVO_TS_PACKET_COPY")) : 1;
+  if (!enabled || !p || n < 4096) return nullptr;                    // small pushes: the copies are not what costs
+  const uint8_t* b[4] = {(const uint8_t*)x, (const uint8_t*)y, (const uint8_t*)t, p};
+  const size_t len[4] = {n * 2, n * 2, n * 8, n};
+  const uint8_t *lo = b[0], *hi = b[0] + len[0];
+  for (int i = 1; i < 4; ++i) { if (b[i] < lo) lo = b[i]; if (b[i] + len[i] > hi) hi = b[i] + len[i]; }
+  span = (size_t)(hi - lo);
+  return span <= n * 13 + 64 ? lo : nullptr;
+}
+
 int ts_push(Ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t* t, const uint8_t* p, size_t n, bool dev_src) {
   if (n == 0) return ESVO_OK;
+  size_t span = 0;
   TsState& s = c->ts[cam];
   int rc = ts_make_room(c, cam, n);
   if (rc) return rc;
@@ -485,6 +498,22 @@ int ts_push(Ctx* c, int cam, const uint16_t* x, const uint16_t* y, const int64_t
   } else if (dev_src) {
     ts_ingest_kernel<<<g, B, 0, c->stream>>>(x, y, t, p, n, s.ex + off, s.ey + off, s.et + off, s.ep + off, gbase, c->dc.W, c->dc.H,
                                              (long long*)s.cur_idx, s.scalars, (const long long*)s.max_t);
+  } else if (const uint8_t* lo = packet_span(x, y, t, p, n, span)) {
+    // The four arrays sit next to each other in host memory (one packet buffer, e.g. t | x | y | p): ONE copy of the whole
+    // span into a landing buffer (same address skew mod 16, so every array keeps its alignment), then the device-source
+    // ingest kernel.  Three copies fewer per push -- the host-buffer path is host-issue-bound.
+    const size_t skew = (size_t)((uintptr_t)lo & 15);
+    if (span + 16 > s.pack_cap) {
+      ESVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      if (s.pack_dev) cudaFree(s.pack_dev);
+      s.pack_cap = std::max<size_t>(2 * (span + 16), (size_t)1 << 20);
+      ESVO_CUDA_TRY(c, dmalloc(&s.pack_dev, s.pack_cap));
+    }
+    uint8_t* d0 = s.pack_dev + skew;
+    ESVO_CUDA_TRY(c, cudaMemcpyAsync(d0, lo, span, cudaMemcpyHostToDevice, c->stream));
+    ts_ingest_kernel<<<g, B, 0, c->stream>>>((const uint16_t*)(d0 + ((const uint8_t*)x - lo)), (const uint16_t*)(d0 + ((const uint8_t*)y - lo)),
+                                             (const int64_t*)(d0 + ((const uint8_t*)t - lo)), d0 + (p - lo), n, s.ex + off, s.ey + off, s.et + off,
+                                             s.ep + off, gbase, c->dc.W, c->dc.H, (long long*)s.cur_idx, s.scalars, (const long long*)s.max_t);
   } else {
     ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ex + off, x, n * 2, cudaMemcpyHostToDevice, c->stream));
     ESVO_CUDA_TRY(c, cudaMemcpyAsync(s.ey + off, y, n * 2, cudaMemcpyHostToDevice, c->stream));

@@ -329,7 +329,10 @@ ESVO_API int esvo_track_get_negative_ts(esvo_ctx* ctx, double* ts_neg, double* d
 
 /* ---------------- device-resident staging (bench "value" leg, pipelines) ---------------- */
 /* Split forms of the host-buffer calls above: stage = H2D only, run = kernels only (async on
- * the ctx stream), fetch = D2H only.  esvo_sync waits for the ctx stream. */
+ * the ctx stream), fetch = D2H only.  esvo_sync waits for the ctx stream.
+ * Event packets: when x, y, t_ns and pol (>= 4096 events) lie next to each other in host memory -- one packet buffer in any
+ * order, at most 64 bytes of padding in total -- esvo_stage_ts_events / esvo_ts_push_events move them with ONE copy instead
+ * of four (the host-buffer path is host-issue-bound); separate allocations work as before. */
 ESVO_API int esvo_stage_ts_events(esvo_ctx* ctx, int cam, const uint16_t* x, const uint16_t* y,
                                   const int64_t* t_ns, const uint8_t* pol, size_t n);
 ESVO_API int esvo_run_ts_build(esvo_ctx* ctx, int cam, int64_t t_sync_ns);

@@ -30,6 +30,39 @@ def test_time_surface_bit_exact(oracle_lib, product_lib, rig):
         assert (to >= 0).all()
 
 
+@pytest.mark.parametrize("order", ["txyp", "xytp", "pad"])
+def test_time_surface_packet_buffer_push(oracle_lib, product_lib, order):
+    """Host pushes whose four arrays are adjacent in memory (one packet buffer) take the single-copy path of ts_push; arrays in
+    separate allocations take four copies.  Same bytes either way, for any order of the arrays inside the packet and with a
+    misaligned packet start."""
+    s = scenario("hkust")
+    o, g = make_backends("hkust", oracle_lib, product_lib)
+    for cam, side in ((0, "left"), (1, "right")):
+        e = s[side]
+        n = e["x"].size
+        half = n // 2
+        for a, b in ((0, half), (half, n)):
+            m = b - a
+            lead = 8 if order == "pad" else 0
+            buf = np.zeros(13 * m + 64, np.uint8)
+            if order == "xytp":
+                ox, oy = lead, lead + 2 * m
+                ot = (oy + 2 * m + 7) // 8 * 8
+                op = ot + 8 * m
+            else:
+                ot = lead
+                ox = ot + 8 * m; oy = ox + 2 * m; op = oy + 2 * m
+            x = buf[ox:ox + 2 * m].view(np.uint16); y = buf[oy:oy + 2 * m].view(np.uint16)
+            t = buf[ot:ot + 8 * m].view(np.int64); p = buf[op:op + m]
+            x[:] = e["x"][a:b]; y[:] = e["y"][a:b]; t[:] = e["t"][a:b]; p[:] = e["p"][a:b]
+            g.ts_push_events(cam, x, y, t, p)                    # one packet
+            o.ts_push_events(cam, e["x"][a:b], e["y"][a:b], e["t"][a:b], e["p"][a:b])
+        for T in (s["t_ts_ns"], int(e["t"][n - 50])):
+            io, to = o.ts_build(cam, T)
+            ig, tg = g.ts_build(cam, T)
+            assert np.array_equal(io, ig) and np.array_equal(to, tg), (order, cam, T)
+
+
 def test_time_surface_queue_depth_quirk(oracle_lib, product_lib):
     """A pixel with >= max_event_queue_len events newer than T yields 'no event' (TimeSurface.h:52-75)."""
     o, g = make_backends("hkust", oracle_lib, product_lib)
