@@ -1172,7 +1172,7 @@ int fuse_finish(Ctx* c, bool naive, const double* clean4) {
   CleanArgs ca{0, 0, 0, 0, 0, 0, 0, 0};
   static const int dbg_phase = getenv("ESVO_DBG_FOLD_PHASE") ? atoi(getenv("ESVO_DBG_FOLD_PHASE")) : 0;
   ca.dbg_phase = dbg_phase;
-  static const int net_sort = getenv("ESVO_FOLD_NETSORT") ? atoi(getenv("ESVO_FOLD_NETSORT")) : 1;   // 0 heap sort, 1 network <= 64, 2 + merged runs <= 192 (experiment)
+  static const int net_sort = getenv("ESVO_FOLD_NETSORT") ? atoi(getenv("ESVO_FOLD_NETSORT")) : 2;   // 0 heap sort, 1 network <= 64, 2 + merged runs <= 192
   ca.net_sort = net_sort;
   static const int fast_div = getenv("ESVO_FOLD_FASTDIV") ? atoi(getenv("ESVO_FOLD_FASTDIV")) : 1;
   ca.fast_div = fast_div;
