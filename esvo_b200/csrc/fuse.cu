@@ -354,6 +354,49 @@ __device__ __forceinline__ void sort_ids(int* ids, int cnt, bool network) {
   else if (network && cnt <= 64) network_sort_local<64>(ids, cnt);
   else heap_sort_i32(ids, cnt);   // O(L log L) on the local array
 }
+// Lists longer than the local array (dense scenes; the 640x480 rig with fusion radius 1): kept out of line so that its
+// registers (run heads of the k-way merge) do not count against the common path.
+template <bool NAIVE>
+__device__ __noinline__ void fold_long_list(const DevConsts& dc, const PropSoA& P, FoldState& f, int row, int col, int h, int total,
+                                            const int32_t* __restrict__ next, int32_t* sort_pool, unsigned long long* scal,
+                                            unsigned long long seq_base, const CleanArgs& clean) {
+  int* seg = sort_pool + atomicAdd(&scal[5], (unsigned long long)total);
+  int k = 0;
+  for (int q = h; q >= 0; q = next[q]) seg[k++] = q;
+  const int nruns = (total + 63) >> 6;
+  if (clean.net_sort >= 3 && nruns <= 32) {
+    // up to 2 048 ids: runs of 64 sorted in place by the register network, then a k-way merge driven by the replay (the
+    // cached heads of the runs are scanned per step) instead of a heap sort with two dependent global accesses per sift
+    for (int r = 0; r < nruns; ++r) network_sort_local<64>(seg + 64 * r, min(64, total - 64 * r));
+    int hpos[32], hval[32];
+    for (int r = 0; r < nruns; ++r) { hpos[r] = 64 * r; hval[r] = seg[64 * r]; }
+    auto pop = [&]() -> int {
+      int best = 0x7fffffff, which = 0;
+      for (int r = 0; r < nruns; ++r) if (hval[r] < best) { best = hval[r]; which = r; }
+      const int p = ++hpos[which];
+      hval[which] = (p < min(64 * (which + 1), total)) ? seg[p] : 0x7fffffff;
+      return best;
+    };
+    int id_cur = pop();
+    FoldRec cur = P.hot[id_cur / 9];
+    for (int a = 0; a < total; ++a) {
+      int id_nxt = id_cur;
+      FoldRec nxt = cur;
+      if (a + 1 < total) { id_nxt = pop(); nxt = P.hot[id_nxt / 9]; }
+      fold_apply<NAIVE>(dc, P, f, row, col, id_cur, cur, seq_base);
+      id_cur = id_nxt; cur = nxt;
+    }
+  } else {
+    sort_ids(seg, total, false);
+    FoldRec cur = P.hot[seg[0] / 9];
+    for (int a = 0; a < total; ++a) {
+      FoldRec nxt = cur;
+      if (a + 1 < total) nxt = P.hot[seg[a + 1] / 9];
+      fold_apply<NAIVE>(dc, P, f, row, col, seg[a], cur, seq_base);
+      cur = nxt;
+    }
+  }
+}
 template <bool NAIVE>
 __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* head, const int32_t* __restrict__ next,
                                  const int32_t* __restrict__ active, int32_t* pcnt, unsigned long long seq_base, unsigned long long* scal,
@@ -375,7 +418,7 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
   FoldState f;
   fold_load(M, pix, row, col, f);
   f.fast = clean.fast_div != 0;
-  if (total <= CAP && cnt > 64 && clean.net_sort == 2) {
+  if (total <= CAP && cnt > 64 && clean.net_sort >= 2) {
     // 65..192 ids: up to three runs of 64, each sorted by the register network, merged on the fly by the replay (the head
     // of every run is compared per step) -- no heap sort in local memory (0.13 of the 0.33 ms the fusion stage takes alone)
     const int e0 = 64, e1 = min(cnt, 128), e2 = cnt;
@@ -414,17 +457,7 @@ __global__ void fuse_fold_kernel(DevConsts dc, MapSoA M, PropSoA P, int32_t* hea
   } else {
     // long list (dense scenes: several hundred contributions on one pixel): its ids go to a private segment of the sort pool
     // (the pool holds one int per contribution, so the segments of all pixels always fit), heap-sorted there, replayed as above
-    int* seg = sort_pool + atomicAdd(&scal[5], (unsigned long long)total);
-    int k = 0;
-    for (int q = h; q >= 0; q = next[q]) seg[k++] = q;
-    sort_ids(seg, total, false);
-    FoldRec cur = P.hot[seg[0] / 9];
-    for (int a = 0; a < total; ++a) {
-      FoldRec nxt = cur;
-      if (a + 1 < total) nxt = P.hot[seg[a + 1] / 9];
-      fold_apply<NAIVE>(dc, P, f, row, col, seg[a], cur, seq_base);
-      cur = nxt;
-    }
+    fold_long_list<NAIVE>(dc, P, f, row, col, h, total, next, sort_pool, scal, seq_base, clean);
   }
   fold_store(dc, M, pix, f, clean, cbits, seq_base, scal);
 }
@@ -1172,7 +1205,7 @@ int fuse_finish(Ctx* c, bool naive, const double* clean4) {
   CleanArgs ca{0, 0, 0, 0, 0, 0, 0, 0};
   static const int dbg_phase = getenv("ESVO_DBG_FOLD_PHASE") ? atoi(getenv("ESVO_DBG_FOLD_PHASE")) : 0;
   ca.dbg_phase = dbg_phase;
-  static const int net_sort = getenv("ESVO_FOLD_NETSORT") ? atoi(getenv("ESVO_FOLD_NETSORT")) : 2;   // 0 heap sort, 1 network <= 64, 2 + merged runs <= 192
+  static const int net_sort = getenv("ESVO_FOLD_NETSORT") ? atoi(getenv("ESVO_FOLD_NETSORT")) : 2;   // 0 heap sort, 1 network <= 64, 2 + merged runs <= 192, 3 + merged runs in the pool (<= 2 048 ids; experiment)
   ca.net_sort = net_sort;
   static const int fast_div = getenv("ESVO_FOLD_FASTDIV") ? atoi(getenv("ESVO_FOLD_FASTDIV")) : 1;
   ca.fast_div = fast_div;
