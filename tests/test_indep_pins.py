@@ -204,6 +204,83 @@ def test_propagate_and_student_t_fusion_vs_numpy(frame):
     assert checked >= 40 and fused >= 40
 
 
+def _grid_vs_map(grid, m, tag):
+    assert len(grid.elements) == m.size, (tag, len(grid.elements), m.size)
+    assert [e.row for e in grid.elements] == m["row"].tolist() and [e.col for e in grid.elements] == m["col"].tolist(), tag + ": element order"
+    assert [e.age for e in grid.elements] == m["age"].tolist(), tag + ": ages"
+    for name, get in (("inv_depth", lambda e: e.rho), ("scale2", lambda e: e.s2), ("nu", lambda e: e.nu), ("variance", lambda e: e.var),
+                      ("residual", lambda e: e.res)):
+        a = np.array([get(e) for e in grid.elements]); b = m[name]
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-300), (tag, name, np.abs(a - b).max())
+    pc = np.array([e.p_cam for e in grid.elements])
+    assert np.allclose(pc, m["p_cam"], rtol=1e-9, atol=1e-12), tag + ": p_cam"
+    xx = np.array([e.x for e in grid.elements])
+    assert np.allclose(xx, m["x"], rtol=1e-12, atol=0), tag + ": x"
+
+
+@pytest.mark.parametrize("radii", [(0, 0, 1), (1, 0, 1)])
+def test_fusion_case_analysis_clean_and_regularisation_vs_python(frame, radii):
+    """The map-side control flow -- DepthFusion::update / fusion with its four cases (create, compatible fuse, occlusion,
+    replace incl. the row_/col_ copy), SmartGrid's insertion order and clean, DepthRegularization::apply with the
+    getNeighbourhood quirk -- against tests/indep_fusion.py, written from the reference sources independently of the oracle:
+    three vectors fused from slightly different poses with fusion radius 0 and 1, then clean, then regularise."""
+    import indep_fusion as inf
+    f = frame
+    o, prm = f["o"], f["prm"]
+    pts, _ = o.depth_solve(f["seeds"])
+    cost_thr = prm.residual_vis_threshold ** 2 * prm.patch_size_x * prm.patch_size_y
+    pts = o.depth_cull(pts, prm.stdvar_vis_threshold, cost_thr, prm.invdepth_min_range, prm.invdepth_max_range)
+    assert pts.size > 400
+    W, H = o.W, o.H
+    T0 = np.asarray(f["s"]["T_world_left"], float)
+    grid = inf.Grid(H, W)
+    rng = np.random.default_rng(1)
+    n_rep = 0
+    for k, radius in enumerate(radii):
+        v = pts.copy()
+        v["T_world_cam"][:, 3] += 0.0015 * k            # shift the observation poses: propagation lands on neighbouring pixels
+        v["T_world_cam"][:, 7] -= 0.001 * k
+        if k == 2:                                       # a vector of confident, low-residual points: exercises the replace branch
+            v["scale2"] *= 0.05; v["variance"] *= 0.05; v["residual"] *= 0.2
+            v["inv_depth"] *= 1.0 + 0.4 * rng.standard_normal(v.size) * (rng.random(v.size) < 0.3)
+            for q in v:                                  # p_cam consistent with the perturbed inverse depth
+                q["p_cam"][:] = ind.cam2world(f["Pl"], q["x"], q["inv_depth"])
+        nf_o = o.fuse(v, T0, radius, reset_map=(k == 0))
+        vec = [dict(p_cam=q["p_cam"], s2=float(q["scale2"]), nu=float(q["nu"]), res=float(q["residual"]), age=int(q["age"]),
+                    T_world_cam=q["T_world_cam"]) for q in v]
+        before = {id(e): (e.row, e.col) for e in grid.elements}
+        nf_p = inf.fuse_vector(grid, vec, T0, f["Pl"], W, H, radius)
+        n_rep += sum(1 for e in grid.elements if id(e) in before and before[id(e)] != (e.row, e.col))
+        assert nf_o == nf_p, (k, nf_o, nf_p)
+        _grid_vs_map(grid, o.map_download(), f"round {k}")
+    assert n_rep > 0, "the replace branch (case 2.2, dm->get(row,col) = dp_prop) was never taken"
+    o.map_clean(prm.stdvar_vis_threshold ** 2, prm.age_vis_threshold, prm.invdepth_max_range, prm.invdepth_min_range)
+    n_before = len(grid.elements)
+    grid.clean(prm.stdvar_vis_threshold ** 2, prm.age_vis_threshold, prm.invdepth_max_range, prm.invdepth_min_range)
+    assert len(grid.elements) < n_before
+    _grid_vs_map(grid, o.map_download(), "clean")
+    o.map_regularize()
+    m = o.map_download()
+    # (a) keyed by the cell that holds the element -- the oracle's and the kernels' documented choice (DESIGN.md deviation 7)
+    grid2 = inf.regularize(grid, prm.reg_radius, prm.reg_min_neighbours, prm.reg_min_close_neighbours, literal=False)
+    _grid_vs_map(grid2, m, "regularise")
+    assert (m["inv_depth"] == -1.0).any() and (m["inv_depth"] > 0).any()
+    # (b) exactly as written: an element whose row_/col_ a replacement copied from another pixel is keyed by the cell it NAMES,
+    # i.e. merged into that cell while its own cell vanishes.  The two differ by those elements only.
+    grid3 = inf.regularize(grid, prm.reg_radius, prm.reg_min_neighbours, prm.reg_min_close_neighbours, literal=True)
+    moved = [k for k, e in grid.cell.items() if (e.row, e.col) != k]
+    assert 0 < len(grid2.elements) - len(grid3.elements) <= len(moved), (len(grid2.elements), len(grid3.elements), len(moved))
+    untouched = {k for k in grid3.cell} - {(grid.cell[k].row, grid.cell[k].col) for k in moved}
+    r = max(prm.reg_radius, 1)
+    far = [k for k in untouched if all(abs(k[0] - q[0]) > r or abs(k[1] - q[1]) > r for q in moved)
+           and all(abs(k[0] - grid.cell[q].row) > r or abs(k[1] - grid.cell[q].col) > r for q in moved)]
+    assert len(far) > 0.5 * len(grid3.elements)
+    for k in far:                                   # away from the re-keyed elements the two readings agree exactly
+        assert grid3.cell[k].rho == grid2.cell[k].rho, k
+    print("regularisation: %d elements, %d with copied coordinates, literal reading merges %d" %
+          (len(grid2.elements), len(moved), len(grid2.elements) - len(grid3.elements)))
+
+
 def test_tracking_residual_and_jacobian_vs_numpy(frame):
     f = frame
     o, prm, s = f["o"], f["prm"], f["s"]
