@@ -393,3 +393,34 @@ def vemp_to_points(matches, Pl, age_vis_threshold):
         out.append(dict(row=int(np.floor(m["x_left"][1])), col=int(np.floor(m["x_left"][0])), x=m["x_left"], inv_depth=m["inv_depth"],
                         variance=1e-6, residual=m["cost"], age=int(age_vis_threshold), p_cam=cam2world(Pl, m["x_left"], m["inv_depth"]), T=m["T"]))
     return out
+
+
+# ---- a1/a2: EventQueueMat (esvo_time_surface/include/esvo_time_surface/TimeSurface.h:28-96) and
+#      TimeSurface::createTimeSurfaceAtTime, BACKWARD mode (esvo_time_surface/src/TimeSurface.cpp:52-152); image ops by OpenCV itself
+def time_surface_backward(ev, T_ns, decay_ms, W, H, ignore_polarity, median_blur_kernel_size, map1, map2, queue_len=20):
+    """ev: dict of x, y, t (ns), p in ARRIVAL order.  Returns (raw mono8 before remap, published mono8 after remap)."""
+    import collections
+    import cv2
+    queues = collections.defaultdict(lambda: collections.deque(maxlen=queue_len))       # insertEvent: push_back, pop_front beyond queueLen
+    for x, y, t, p in zip(ev["x"].tolist(), ev["y"].tolist(), ev["t"].tolist(), ev["p"].tolist()):
+        if 0 <= x < W and 0 <= y < H:
+            queues[(x, y)].append((t, p))
+    decay_sec = decay_ms / 1000.0
+    m = np.zeros((H, W), np.float64)
+    for (x, y), q in queues.items():
+        for t, p in reversed(q):                                                          # getMostRecentEventBeforeT: newest first, ts < T
+            if t < T_ns:
+                if ros_to_sec(t) > 0:
+                    d = T_ns - t                                                          # ros::Duration (integer ns), then toSec()
+                    dt = float(d // 1000000000) + 1e-9 * float(d % 1000000000)
+                    v = np.exp(-dt / decay_sec)
+                    if not ignore_polarity:
+                        v *= 1.0 if p else -1.0
+                    m[y, x] = v
+                break
+    m = 255.0 * m if ignore_polarity else 255.0 * (m + 1.0) / 2.0
+    img = np.clip(np.rint(m), 0, 255).astype(np.uint8)                                    # convertTo(CV_8U): saturate_cast(cvRound), half to even
+    if median_blur_kernel_size > 0:
+        img = cv2.medianBlur(img, 2 * median_blur_kernel_size + 1)
+    out = cv2.remap(img, map1, map2, cv2.INTER_LINEAR)
+    return img, out

@@ -204,6 +204,31 @@ def test_propagate_and_student_t_fusion_vs_numpy(frame):
     assert checked >= 40 and fused >= 40
 
 
+@pytest.mark.parametrize("rig,polarity,median", [("hkust", True, 1), ("hkust", False, 0), ("dsec", True, 1)])
+def test_time_surface_backward_vs_numpy_and_cv2(oracle_lib, rig, polarity, median):
+    """a1/a2: the per-pixel event queues (20 deep, newest entry before T wins, nothing if all 20 are newer) and the BACKWARD
+    raster (decay, mono8 rounding, 3x3 median, remap) of the oracle against an independent re-derivation whose image operations
+    are OpenCV's own (tests/indep_numpy.py::time_surface_backward): published image bit for bit, for T newer than every stamp
+    and for T inside the stream."""
+    pytest.importorskip("cv2")
+    s = scenario(rig, seed=2, n_seeds=100)
+    l, r = configs.rig_calibs(rig)
+    prm = configs.params_for(rig, oracle_lib)
+    prm.ignore_polarity = 1 if polarity else 0
+    prm.median_blur_kernel_size = median
+    o = capi.Backend(oracle_lib, l, r, prm)
+    for cam, side in ((0, "left"), (1, "right")):
+        e = s[side]
+        o.ts_push_events(cam, e["x"], e["y"], e["t"], e["p"])
+        m1, m2, _, _ = o.get_rectify_tables(cam)
+        n = e["t"].size
+        for T in (s["t_ts_ns"], int(e["t"][n // 2]), int(e["t"][n // 5])):
+            _, ts = o.ts_build(cam, T, want_idx=False)
+            _, ref = ind.time_surface_backward(e, T, prm.decay_ms, o.W, o.H, bool(prm.ignore_polarity), median, m1, m2, prm.max_event_queue_len)
+            assert np.array_equal(ts, ref), (rig, cam, T, int((ts != ref).sum()))
+        assert ts.max() > 0
+
+
 def _grid_vs_map(grid, m, tag):
     assert len(grid.elements) == m.size, (tag, len(grid.elements), m.size)
     assert [e.row for e in grid.elements] == m["row"].tolist() and [e.col for e in grid.elements] == m["col"].tolist(), tag + ": element order"
