@@ -424,3 +424,73 @@ def time_surface_backward(ev, T_ns, decay_ms, W, H, ignore_polarity, median_blur
         img = cv2.medianBlur(img, 2 * median_blur_kernel_size + 1)
     out = cv2.remap(img, map1, map2, cv2.INTER_LINEAR)
     return img, out
+
+
+# ---- a4: EventBM::match_an_event / match_all_HyperThread / match (esvo_core/src/core/EventBM.cpp:80-168,269-315) ----
+def event_bm_match_all(ev, ts_l, ts_r, lut_l, mask_l, pose_t, poses, wx, wy, dmin, dmax, step, thr, baseline, P00, num_thread):
+    """ev: dict x, y, t of the events handed to createMatchProblem (left camera, raw pixels).  Returns the EventMatchPairs (dicts)
+    in the reference's thread-major order and the number of zncc evaluations.  Left-right rig only (bUpDownConfiguration false)."""
+    H, W = ts_l.shape
+    hx, hy = (wx - 1) // 2, (wy - 1) // 2
+    tsl = ts_l.astype(np.float64); tsr = ts_r.astype(np.float64)
+    pose_sec = np.array([ros_to_sec(t) for t in pose_t])
+    evals = 0
+
+    def valid(x, y):                                                   # isValidPatch (:251-267)
+        return not (x - hx < 1 or y - hy < 1 or x + hx >= W - 1 or y + hy >= H - 1)
+
+    def search(x1, patch, start, end, sstep, state):                   # epipolarSearching (:170-226)
+        nonlocal evals
+        costs = {}
+        d = start
+        while d <= end:
+            x2 = x1[0] - d
+            if not valid(x2, x1[1]):
+                costs[d] = 1.0
+            else:
+                c = zncc_cost(patch, tsr[x1[1] - hy:x1[1] + hy + 1, x2 - hx:x2 + hx + 1])
+                evals += 1
+                costs[d] = c
+                if c <= state["min"]:
+                    state.update(min=c, bx=x2, bd=d)
+            d += sstep
+        if sstep > 1:
+            lo, hi = state["bd"] - sstep, state["bd"] + sstep
+            return lo in costs and hi in costs and costs[lo] < 1.0 and costs[hi] < 1.0 and state["min"] < thr
+        return state["min"] < thr
+
+    def one(i):
+        xr = lut_l[int(ev["y"][i]), int(ev["x"][i])]
+        if xr[0] < 0 or xr[0] > W - 1 or xr[1] < 0 or xr[1] > H - 1:
+            return None
+        if mask_l[int(xr[1]), int(xr[0])] <= 125:                      # Eigen's (double) index: truncation
+            return None
+        x1 = (int(np.floor(xr[0])), int(np.floor(xr[1])))
+        if not valid(*x1):
+            return None
+        patch = tsl[x1[1] - hy:x1[1] + hy + 1, x1[0] - hx:x1[0] + hx + 1]
+        if (patch < 1).sum() > 0.95 * patch.size:                      # low information-to-noise ratio (:104-109)
+            return None
+        st = dict(min=1.0, bx=0, bd=0)
+        if not search(x1, patch, dmin, dmax, step, st):                # coarse
+            return None
+        if not search(x1, patch, st["bd"] - (step - 1), st["bd"] + (step - 1), 1, st):     # fine
+            return None
+        if not st["min"] <= thr:
+            return None
+        disparity = float(x1[0] - st["bx"])
+        k = int(np.searchsorted(pose_sec, ros_to_sec(ev["t"][i]), side="left"))             # StampTransformationMap_lower_bound on toSec()
+        if k == len(pose_t):
+            return None
+        depth = baseline * P00 / disparity
+        return dict(i=i, x_left_raw=(float(ev["x"][i]), float(ev["y"][i])), x_left=xr, x_right=(float(st["bx"]), float(x1[1])), t_ns=int(ev["t"][i]),
+                    pose=k, inv_depth=1.0 / depth, cost=st["min"], disp=disparity)
+
+    out = []
+    n = len(ev["x"])
+    for tid in range(num_thread):                                      # match (:300-315): thread tid takes events tid, tid + NT, ...
+        for i in range(tid, n, num_thread):
+            m = one(i)
+            if m is not None:
+                out.append(m)
+    return out, evals

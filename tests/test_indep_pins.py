@@ -54,6 +54,66 @@ def test_bm_cost_and_disparity_vs_numpy(frame):
         assert sd["x_right"][0] == x1[0] - d and sd["x_right"][1] == x1[1]
 
 
+def test_event_bm_accept_set_and_order_vs_numpy(frame):
+    """a4: which events EventBM accepts (image bounds, mask, patch validity, the 95 % low-information rule, coarse / fine search,
+    threshold, pose look-up), in which ORDER they come out (4 interleaved threads, results concatenated per thread) and every field
+    of the EventMatchPair -- the oracle against tests/indep_numpy.py::event_bm_match_all, written from EventBM.cpp independently."""
+    f = frame
+    o, s, prm = f["o"], f["s"], f["prm"]
+    sd = s["seeds"]
+    _, _, lut, mask = o.get_rectify_tables(0)
+    d = f["d"]
+    ref, evals = ind.event_bm_match_all(sd, f["tl"], f["tr"], lut, mask, s["pose_t"], s["poses"], prm.patch_size_x, prm.patch_size_y, d["min_disparity"],
+                                        d["max_disparity"], prm.bm_step, prm.bm_zncc_threshold, d["baseline"], f["Pl"][0, 0], prm.num_thread_mapping)
+    seeds, evals_o = o.bm_match(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+    assert len(ref) == seeds.size and len(ref) > 400, (len(ref), seeds.size)
+    assert evals == evals_o
+    for q, m in zip(seeds, ref):
+        assert q["t_ns"] == m["t_ns"] and tuple(q["x_left_raw"]) == m["x_left_raw"]
+        assert np.array_equal(q["x_left"], m["x_left"]) and tuple(q["x_right"]) == m["x_right"] and q["disp"] == m["disp"]
+        assert abs(q["cost"] - m["cost"]) < 1e-12 and abs(q["inv_depth"] - m["inv_depth"]) <= 4e-16 * m["inv_depth"]
+        assert np.array_equal(q["T_world_virtual"], np.asarray(s["poses"][m["pose"]], float).ravel())
+    # the rejection paths are all exercised by this scenario
+    assert seeds.size < sd["x"].size
+
+
+def test_solver_output_conversion_order_and_culling_vs_numpy(frame):
+    """a10: what DepthProblemSolver does around the per-seed LM (DepthProblemSolver.cpp:28-135,217-244) -- results of the 4
+    interleaved jobs concatenated per thread, seeds whose solution is <= 0.001 dropped, DepthPoint(row = floor(y), col = floor(x)),
+    x, p_cam = cam2World(x, rho), Student-t scale from the variance, pose; and pointCulling's predicate and order."""
+    f = frame
+    o, prm = f["o"], f["prm"]
+    seeds = f["seeds"]
+    pts, _ = o.depth_solve(seeds)
+    NT = prm.num_thread_mapping
+    order = [i for tid in range(NT) for i in range(tid, seeds.size, NT)]
+    # every output point corresponds to a seed, in thread-major order, no seed twice
+    key = lambda a: (float(a[0]), float(a[1]))
+    it = iter(order)
+    used = []
+    for p in pts:
+        for i in it:
+            if key(seeds[i]["x_left"]) == key(p["x"]) and np.array_equal(seeds[i]["T_world_virtual"], p["T_world_cam"]):
+                used.append(i); break
+        else:
+            raise AssertionError("output point without a seed later in the thread-major order")
+    assert len(used) == pts.size and pts.size >= 0.95 * seeds.size
+    nu = prm.td_nu
+    for p, i in zip(pts[:400], used[:400]):
+        sd = seeds[i]
+        assert p["row"] == int(np.floor(sd["x_left"][1])) and p["col"] == int(np.floor(sd["x_left"][0]))
+        assert p["inv_depth"] > 0.001 and p["nu"] == nu and p["age"] == 0
+        assert abs(p["scale2"] - p["variance"] * (nu - 2) / nu) <= 1e-15 * p["scale2"]
+        pc = ind.cam2world(f["Pl"], sd["x_left"], p["inv_depth"])
+        assert np.abs(p["p_cam"] - pc).max() <= 1e-12 * np.abs(pc).max()
+    # pointCulling
+    cost_thr = prm.residual_vis_threshold ** 2 * prm.patch_size_x * prm.patch_size_y
+    culled = o.depth_cull(pts, prm.stdvar_vis_threshold, cost_thr, prm.invdepth_min_range, prm.invdepth_max_range)
+    keep = (pts["variance"] <= prm.stdvar_vis_threshold ** 2) & (pts["residual"] <= cost_thr) & (pts["inv_depth"] > -1e-6) & \
+           (pts["inv_depth"] >= prm.invdepth_min_range) & (pts["inv_depth"] <= prm.invdepth_max_range)
+    assert 0 < keep.sum() < pts.size and culled.tobytes() == pts[keep].tobytes()
+
+
 def _T_left_virtual(f, sd):
     T_left_world = np.linalg.inv(np.asarray(f["s"]["T_world_left"], float))
     return T_left_world @ sd["T_world_virtual"].reshape(4, 4)
