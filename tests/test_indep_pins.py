@@ -114,6 +114,63 @@ def test_solver_output_conversion_order_and_culling_vs_numpy(frame):
     assert 0 < keep.sum() < pts.size and culled.tobytes() == pts[keep].tobytes()
 
 
+@pytest.mark.parametrize("strategy", ["CONST_FRAMES", "CONST_POINTS"])
+def test_mapping_at_time_window_bookkeeping_vs_python(oracle_lib, strategy):
+    """esvo_Mapping::MappingAtTime (esvo_Mapping.cpp:261-399) as a Python sequence over the separately pinned stages -- block
+    matching, solve, culling, window push with the CONST_FRAMES / CONST_POINTS eviction rules, fusion newest first, clean only
+    once the window holds maxNumFusionFrames vectors, regularisation -- against the oracle's single call, five frames."""
+    l, r = configs.rig_calibs(RIG)
+
+    def backend():
+        p = configs.params_for(RIG, oracle_lib)
+        p.max_num_fusion_frames = 3
+        p.fusion_strategy = capi.FUSION_CONST_POINTS if strategy == "CONST_POINTS" else capi.FUSION_CONST_FRAMES
+        p.max_num_fusion_points = 600
+        return capi.Backend(oracle_lib, l, r, p), p
+    a, prm = backend()       # the single call
+    b, _ = backend()         # the stages
+    window = []
+    sizes = []
+    for k, t_ts in enumerate((0.50, 0.52, 0.54, 0.56, 0.58)):
+        s = scenario(RIG, seed=2, n_seeds=600, t_ts=t_ts)
+        tl, tr = build_ts_pair(a, s)
+        a.ts_reset(0); a.ts_reset(1)
+        sd = s["seeds"]
+        a.set_ts_pair(tl, tr, s["T_world_left"]); b.set_ts_pair(tl, tr, s["T_world_left"])
+        ca = a.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+        # ---- the same frame, stage by stage ----
+        vemp, _ = b.bm_match(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+        vdp, _ = b.depth_solve(vemp)
+        cost_thr = prm.residual_vis_threshold ** 2 * prm.patch_size_x * prm.patch_size_y
+        vdp = b.depth_cull(vdp, prm.stdvar_vis_threshold, cost_thr, prm.invdepth_min_range, prm.invdepth_max_range)
+        window.append(vdp)
+        if strategy == "CONST_POINTS":
+            while sum(v.size for v in window) > 1.5 * prm.max_num_fusion_points:
+                window.pop(0)
+        else:
+            while len(window) > prm.max_num_fusion_frames:
+                window.pop(0)
+        nf = 0
+        for q, v in enumerate(reversed(window)):
+            nf += b.fuse(v, s["T_world_left"], prm.fusion_radius, q == 0)
+        if len(window) >= prm.max_num_fusion_frames:
+            b.map_clean(prm.stdvar_vis_threshold ** 2, prm.age_vis_threshold, prm.invdepth_max_range, prm.invdepth_min_range)
+        if prm.regularization:
+            b.map_regularize()
+        ma, mb = a.map_download(), b.map_download()
+        assert ca["n_seeds"] == vemp.size and ca["n_culled"] == vdp.size and ca["n_fusions"] == nf, (k, ca, vemp.size, vdp.size, nf)
+        assert ma.tobytes() == mb.tobytes(), (strategy, k, ma.size, mb.size)
+        sizes.append(len(window))
+        for j in range(len(window)):
+            assert a.window_download(j).tobytes() == window[j].tobytes()
+        with pytest.raises(capi.EsvoError):
+            a.window_download(len(window))
+    if strategy == "CONST_FRAMES":
+        assert sizes == [1, 2, 3, 3, 3]
+    else:
+        assert max(sizes) < 5 and sizes[-1] <= sizes[-2] + 1 and any(sizes[i + 1] <= sizes[i] for i in range(len(sizes) - 1)), sizes
+
+
 def _T_left_virtual(f, sd):
     T_left_world = np.linalg.inv(np.asarray(f["s"]["T_world_left"], float))
     return T_left_world @ sd["T_world_virtual"].reshape(4, 4)
@@ -398,6 +455,77 @@ def test_tracking_residual_and_jacobian_vs_numpy(frame):
         scale = np.abs(J).max()
         assert scale > 0 and np.abs(J - fjac).max() < 1e-10 * scale, np.abs(J - fjac).max()
     assert (fvec != 255).mean() > 0.5
+
+
+def test_tracking_outer_iteration_is_a_minpack_lm_step(frame, oracle_lib):
+    """a19: one pass of RegProblemSolverLM::solve_analytical's loop (RegProblemSolverLM.cpp:150-171) -- batch sampling, x = 0,
+    minimizeInit + ONE minimizeOneStep, addMotionUpdate (RegProblemLM.cpp:349-360), setPose (:362-368) -- checked through what
+    MINPACK's lmder specifies for the first step from x = 0 rather than through a second restatement of lmpar: the step x recovered
+    from the oracle's pose must solve (J^T J + par D^2) x = -J^T f for ONE par >= 0 (D = column norms of J), lie on the initial
+    trust region ||D x|| = delta = factor = 100 within lmpar's 10 % when par > 0, and pass the ratio test.  J and f come from the
+    tap that tests/indep_numpy.py pins; the Cayley / pose algebra is inverted in numpy."""
+    f = frame
+    s = f["s"]
+    l, r = configs.rig_calibs(RIG)
+    prm = configs.params_for(RIG, oracle_lib)
+    prm.trk_max_iteration = 1
+    o = capi.Backend(oracle_lib, l, r, prm)
+    tl, tr = f["tl"], f["tr"]
+    o.set_ts_pair(tl, tr, s["T_world_left"])
+    sd = s["seeds"]
+    o.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+    m = o.map_download()
+    Tw = np.asarray(s["T_world_left"], float)
+    cloud = (m["p_cam"] @ Tw[:3, :3].T + Tw[:3, 3]).astype(np.float32)
+    Tc = Tw.copy(); Tc[:3, 3] += [0.002, 0.001, -0.0015]
+    fn = o.L.lib.esvo_oracle_op_track_eval
+    fn.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 5 + [C.c_int]
+    fn.restype = C.c_int
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    cap = prm.trk_batch_size
+    _, _, _, mask = o.get_rectify_tables(0)
+    o.track_srand(1)
+    assert o.track_reset(cloud.copy(), Tw, Tc, tl) == 0
+    neg, du, dv = o.track_get_negative_ts()
+    fvec = np.zeros(cap); fjac = np.zeros((cap, 6)); pts = np.zeros((cap, 3)); Rt = np.zeros(12)
+    assert fn(o.ctx, P(np.zeros(6)), P(fvec), P(fjac), P(pts), P(Rt), cap) == cap
+    R_, t_ = Rt[:9].reshape(3, 3).copy(), Rt[9:].copy()
+    # the solver itself, one iteration, same batch (same rand() stream)
+    o.track_srand(1)
+    assert o.track_reset(cloud.copy(), Tw, Tc, tl) == 0
+    T, st = o.track_solve(True)
+    assert st["n_iter"] == 1 and st["nfev"] >= 2
+    # invert setPose and addMotionUpdate: R_new = Rw^T R(T), t_new = Rw^T (t(T) - tw); dR = R_new R_^T; Gibbs vector of dR; dt
+    R_new = Tw[:3, :3].T @ T[:3, :3]
+    t_new = Tw[:3, :3].T @ (T[:3, 3] - Tw[:3, 3])
+    dR = R_new @ R_.T
+    assert np.abs(dR @ dR.T - np.eye(3)).max() < 1e-12
+    A = (dR - dR.T) / (1.0 + np.trace(dR))
+    c = np.array([A[2, 1], A[0, 2], A[1, 0]])
+    assert np.abs(ind.cayley2rot(c) - dR).max() < 1e-12
+    x = np.concatenate([c, t_new - dR @ t_])
+    assert np.linalg.norm(x) > 1e-6
+    # (i) a Levenberg-Marquardt step: J^T J x + J^T f = -par D^2 x for one par >= 0
+    D = np.linalg.norm(fjac, axis=0); D[D == 0] = 1.0
+    lhs = fjac.T @ (fjac @ x) + fjac.T @ fvec
+    d2x = D * D * x
+    par = -float(lhs @ d2x) / float(d2x @ d2x)
+    assert par >= -1e-12
+    assert np.linalg.norm(lhs + par * d2x) <= 1e-7 * np.linalg.norm(fjac.T @ fvec), (par, np.linalg.norm(lhs + par * d2x))
+    # (ii) on the trust region of the first iteration (delta = factor * ||D x0|| = 0 -> factor), unless the Gauss-Newton step is inside it
+    dxn = np.linalg.norm(D * x)
+    gn = np.linalg.lstsq(fjac, -fvec, rcond=None)[0]
+    if np.linalg.norm(D * gn) <= 1.1 * 100.0:
+        assert par < 1e-9 and np.abs(x - gn).max() < 1e-9
+    else:
+        assert par > 0 and 0.9 * 100.0 <= dxn <= 1.1 * 100.0, (par, dxn)
+    # (iii) the accepted trial passes the ratio test of lmder (actred / prered >= 1e-4)
+    f1 = ind.track_residuals(x, pts, R_, t_, f["Pl"], mask, neg, prm.trk_huber_threshold)
+    fn0, fn1 = np.linalg.norm(fvec), np.linalg.norm(f1)
+    actred = 1 - (fn1 / fn0) ** 2 if 0.1 * fn1 < fn0 else -1.0
+    prered = (np.linalg.norm(fjac @ x) / fn0) ** 2 + 2 * par * (dxn / fn0) ** 2
+    assert prered > 0 and actred / prered >= 1e-4, (actred, prered)
+    print("tracking LM step: par %.3g, ||D x|| %.2f, actred %.3g, prered %.3g, nfev %d" % (par, dxn, actred, prered, st["nfev"]))
 
 
 def test_cayley_and_J_G_kats():
