@@ -2,9 +2,12 @@
 // C entry points of the CPU restatement; same signatures as include/esvo_b200.h with the prefix
 // esvo_oracle_.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference legs
 // may load this library.  PARITY STATUS: the reference has no tests or golden vectors and cannot
-// be compiled here (needs ROS/Eigen/OpenCV C++), so this restatement is pinned only on its
-// third-party pieces (cv2 4.13, scipy MINPACK, libc rand) and closed-form KATs: "parity unpinned"
-// against the reference binary itself.
+// be compiled here (needs ROS/Eigen/OpenCV C++): "parity unpinned" against the reference binary
+// itself.  What pins this restatement instead: its third-party pieces against cv2 4.13,
+// scipy's MINPACK and libc rand; closed-form KATs; and, stage by stage, INDEPENDENT numpy / Python
+// re-derivations written from the reference sources (tests/indep_numpy.py, tests/indep_fusion.py:
+// time surface, EventBM accept set and order, DepthProblem residual, solver output, fusion case
+// analysis, clean, regularisation, window bookkeeping, tracking residual / Jacobian / LM step, EventMatcher).
 #include <chrono>
 #include <cstdio>
 #include <deque>
