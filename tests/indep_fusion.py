@@ -167,3 +167,41 @@ def regularize(grid, radius, min_nb, min_close, literal=True):
         if not is_set:
             new.rho = -1.0
     return tmp
+
+
+def naive_propagate_vector(grid, pts, T_world_frame, Pl, W, H):
+    """DepthFusion::naive_propagation (DepthFusion.cpp:232-288) with naive_propagate_one_point (:290-327): Gaussian propagation,
+    the four pixels around the re-projection, an empty pixel takes the point, an occupied one keeps the closer estimate and is
+    replaced only by a propagated point with a smaller residual.  pts: dicts p_cam, var, res, age, T_world_cam."""
+    T_frame_world = np.linalg.inv(np.asarray(T_world_frame, float).reshape(4, 4))
+    for p in pts:
+        T = T_frame_world @ np.asarray(p["T_world_cam"], float).reshape(4, 4)
+        pc = np.asarray(p["p_cam"], float)
+        pp = T[:3, :3] @ pc + T[:3, 3]
+        h = Pl[:, :3] @ pp + Pl[:, 3]
+        x = h[:2] / h[2]
+        if x[0] < 0 or x[0] >= W or x[1] < 0 or x[1] >= H:
+            continue
+        prop = Pt(int(math.floor(x[1])), int(math.floor(x[0])))
+        prop.x = x
+        den = (T[2, :2] @ pc[:2] + T[2, 3]) / pc[2] + T[2, 2]
+        J = T[2, 2] / den ** 2
+        prop.rho, prop.var = 1.0 / pp[2], max(J * J * p["var"], 1e-6)      # DepthPoint::update on a fresh point + boundVariance (:140-164)
+        prop.p_cam, prop.res, prop.age = pp, p["res"], p["age"]
+        for dy in (0, 1):
+            for dx in (0, 1):
+                r, c = prop.row + dy, prop.col + dx
+                if c >= W or r >= H:
+                    continue
+                if not grid.exists(r, c):                                   # case 1
+                    nw = Pt(r, c)
+                    nw.rho, nw.var = prop.rho, max(prop.var, 1e-6)
+                    nw.res, nw.age = prop.res, prop.age
+                    nw.p_cam = ind.cam2world(Pl, nw.x, prop.rho)
+                    grid.set(r, c, nw)
+                else:                                                       # case 2
+                    cur = grid.cell[(r, c)]
+                    if cur.rho > prop.rho:
+                        continue
+                    if prop.res < cur.res:
+                        grid.assign(r, c, prop)

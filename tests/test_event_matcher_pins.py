@@ -70,12 +70,28 @@ def test_vemp_to_points_vs_numpy(frame):
 
 
 def test_naive_propagation_of_matched_points(frame):
-    """Mode PURE_EVENT_MATCHING downstream of the matcher (esvo_MVStereo.cpp:272-286): the points splat into an empty frame;
-    nearest wins, so every map element carries the inverse depth of the closest point that landed on its pixel."""
+    """Mode PURE_EVENT_MATCHING downstream of the matcher (esvo_MVStereo.cpp:272-286): two vectors of matched points (the second
+    from a shifted pose) splat into the frame, newest first -- the oracle against the independent Python re-derivation of
+    DepthFusion::naive_propagation (tests/indep_fusion.py): element order, coordinates, values."""
+    import indep_fusion as inf
     f = frame; o = f["o"]
     seeds, _ = o.em_match(f["left"], f["right"], f["counts"], f["poses"])
     pts = o.seeds_to_points(seeds)
-    o.naive_propagate(pts, f["s"]["T_world_left"], True)
-    m = o.map_download()
-    assert 0 < m.size <= 4 * pts.size
-    assert (m["inv_depth"] > 0).all() and (m["variance"] > 0).all()
+    older = pts.copy()
+    older["T_world_cam"][:, 3] += 0.004; older["T_world_cam"][:, 11] -= 0.003
+    older["residual"] *= np.where(np.arange(older.size) % 3 == 0, 0.2, 1.0)      # some of them win the replacement test
+    Pl = configs.rig_arrays(RIG)["left"]["P"]
+    T = f["s"]["T_world_left"]
+    grid = inf.Grid(o.H, o.W)
+    for k, v in enumerate((pts, older)):
+        o.naive_propagate(v, T, k == 0)
+        vec = [dict(p_cam=q["p_cam"], var=float(q["variance"]), res=float(q["residual"]), age=int(q["age"]), T_world_cam=q["T_world_cam"]) for q in v]
+        inf.naive_propagate_vector(grid, vec, T, Pl, o.W, o.H)
+        m = o.map_download()
+        assert len(grid.elements) == m.size and m.size > 100
+        assert [e.row for e in grid.elements] == m["row"].tolist() and [e.col for e in grid.elements] == m["col"].tolist()
+        for name, get in (("inv_depth", lambda e: e.rho), ("variance", lambda e: e.var), ("residual", lambda e: e.res)):
+            assert np.allclose(np.array([get(e) for e in grid.elements]), m[name], rtol=1e-10, atol=0), (k, name)
+        assert [e.age for e in grid.elements] == m["age"].tolist()
+        assert np.allclose(np.array([e.p_cam for e in grid.elements]), m["p_cam"], rtol=1e-9, atol=1e-12)
+    assert any((e.row, e.col) != k for k, e in grid.cell.items()), "no replacement happened"
