@@ -673,7 +673,6 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_solve_kernel(DevConsts dc, Tr
     __syncthreads();
     iteration++;
     nfev_total += nfev;
-    if (!a.analytical) break;                     // solve_numerical's unconditional break (RegProblemSolverLM.cpp:137)
     if (status == 2 || status == 3) break;
   }
   // ---- setPose (:362-372) + statistics ----

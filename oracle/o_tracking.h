@@ -291,7 +291,6 @@ struct RegProblem {
       addMotionUpdate(x.data());
       iteration++;
       nfev += lm.nfev;
-      if (!analytical) break;                     // solve_numerical's unconditional break (:137)
       if (status == 2 || status == 3) break;
     }
     setPose();
