@@ -333,9 +333,10 @@ inline void selectCloseEvents(std::vector<esvo::Event>& events_left /* time-orde
   if (events_left.empty()) return;
   const double t_end = toSec(t_end_ns);
   const int64_t t_begin_ns = fromSec(std::max(0.0, t_end - 10 * BM_half_slice_thickness));
-  auto lower = [&](int64_t t) {   // tools::EventBuffer_lower_bound (utils.h:50-55): ros::Time (integer) comparison
+  auto lower = [&](int64_t t) {   // tools::EventBuffer_lower_bound (utils.h:50-55): compares toSec() DOUBLES (stamps that share a double are equal)
+    const double ts = toSec(t);
     size_t lo = 0, hi = events_left.size();
-    while (lo < hi) { size_t mid = (lo + hi) / 2; if (events_left[mid].ts < t) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (toSec(events_left[mid].ts) < ts) lo = mid + 1; else hi = mid; }
     return lo;
   };
   size_t ev_end = lower(t_end_ns);
@@ -359,8 +360,9 @@ inline void selectSGMEvents(std::vector<esvo::Event>& events_left, int64_t t_end
   if (events_left.empty()) return;
   const int64_t t_begin_ns = fromSec(std::max(0.0, toSec(t_end_ns) - 2 * BM_half_slice_thickness));
   auto lower = [&](int64_t t) {
+    const double ts = toSec(t);
     size_t lo = 0, hi = events_left.size();
-    while (lo < hi) { size_t mid = (lo + hi) / 2; if (events_left[mid].ts < t) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (toSec(events_left[mid].ts) < ts) lo = mid + 1; else hi = mid; }
     return lo;
   };
   size_t ev_end = lower(t_end_ns);
@@ -734,9 +736,10 @@ class esvo_Tracking {
   std::vector<esvo::Pose> lPose_;
   core::RegProblemSolverLM rpSolver_;
  private:
-  size_t lower_bound_ev(int64_t t) const {   // tools::EventBuffer_lower_bound (utils.h:50-55)
+  size_t lower_bound_ev(int64_t t) const {   // tools::EventBuffer_lower_bound (utils.h:50-55): toSec() doubles
+    const double ts = frontend::toSec(t);
     size_t lo = 0, hi = events_left_.size();
-    while (lo < hi) { size_t mid = (lo + hi) / 2; if (events_left_[mid].ts < t) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (frontend::toSec(events_left_[mid].ts) < ts) lo = mid + 1; else hi = mid; }
     return lo;
   }
   struct TsEntry { std::vector<uint8_t> left; size_t id; };

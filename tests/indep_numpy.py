@@ -263,11 +263,28 @@ def select_close_events(t_events, t_end_ns, half_slice, process_event_num):
     or PROCESS_EVENT_NUM pushes.  When no event is at/after t_end the reference's first push reads the slot one past the newest
     event (deque::end()); that slot is skipped here but still counts against PROCESS_EVENT_NUM (include/esvo_b200/esvo_core.hpp)."""
     t_events = np.asarray(t_events, np.int64)
+    secs = np.array([ros_to_sec(t) for t in t_events])                    # EventBuffer_lower_bound compares toSec() doubles (utils.h:50-55)
     t_begin_ns = ros_from_sec(max(0.0, ros_to_sec(t_end_ns) - 10 * half_slice))
-    ev_end = int(np.searchsorted(t_events, t_end_ns, side="left"))
-    ev_begin = int(np.searchsorted(t_events, t_begin_ns, side="left"))
+    ev_end = int(np.searchsorted(secs, ros_to_sec(t_end_ns), side="left"))
+    ev_begin = int(np.searchsorted(secs, ros_to_sec(t_begin_ns), side="left"))
     out, budget = [], process_event_num
     if ev_end == t_events.size and ev_end != ev_begin and budget > 0:
+        ev_end -= 1; budget -= 1
+    while ev_end != ev_begin and len(out) < budget:
+        out.append(ev_end); ev_end -= 1
+    return np.array(out, np.int64)
+
+
+def select_sgm_events(t_events, t_end_ns, half_slice, process_event_num):
+    """The INITIALIZATION branch of dataTransferring (:538-552): window 2 * BM_half_slice_thickness, `<=` on the count (one event
+    more than PROCESS_EVENT_NUM); the one-past-the-end slot is skipped like in select_close_events."""
+    t_events = np.asarray(t_events, np.int64)
+    secs = np.array([ros_to_sec(t) for t in t_events])
+    t_begin_ns = ros_from_sec(max(0.0, ros_to_sec(t_end_ns) - 2 * half_slice))
+    ev_end = int(np.searchsorted(secs, ros_to_sec(t_end_ns), side="left"))
+    ev_begin = int(np.searchsorted(secs, ros_to_sec(t_begin_ns), side="left"))
+    out, budget = [], process_event_num + 1
+    if ev_end == t_events.size and ev_end != ev_begin:
         ev_end -= 1; budget -= 1
     while ev_end != ev_begin and len(out) < budget:
         out.append(ev_end); ev_end -= 1

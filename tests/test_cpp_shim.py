@@ -264,3 +264,41 @@ def test_multi_stream_nccl_gather_matches_python_records(oracle_lib, product_lib
         assert np.array_equal(recs[rank][:7], rec[:7]) and recs[rank][8] == rec[8], (rank, recs[rank], rec)
         assert abs(recs[rank][7] - rec[7]) <= 0.01 * rec[7]                                  # lm_evals (nfev-style counter)
         assert abs(recs[rank][9] - rec[9]) <= 1e-9 * abs(rec[9]), (rank, recs[rank][9], rec[9])
+
+
+@pytest.mark.parametrize("epoch_ns", [0, 1600000000 * 10**9])
+def test_frontend_selections_vs_numpy(tmp_path, epoch_ns):
+    """examples/frontend_dump.cpp: what esvo_core::frontend selects from an event buffer (selectCloseEvents, selectSGMEvents,
+    samplePoseStamps, eventSlicingForEM) against the independent numpy re-derivation of esvo_Mapping::dataTransferring /
+    esvo_MVStereo::eventSlicingForEM (tests/indep_numpy.py) -- also with UNIX-epoch stamps, where ros::Time::toSec() collapses
+    neighbouring nanosecond stamps into one double and the lower bounds compare those doubles."""
+    import struct
+    import numpy as np
+    import indep_numpy as ind
+    exe = str(tmp_path / "frontend_dump")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "frontend_dump.cpp"), "-o", exe])
+    rng = np.random.default_rng(3)
+    n = 40000
+    t = epoch_ns + np.cumsum(rng.integers(1, 900, n)).astype(np.int64)          # ~0.45 us apart: several stamps per double at epoch scale
+    for t_end, half_slice, pen in ((int(t[n // 2]), 0.001, 5000), (int(t[-1]) + 1000, 0.001, 3000), (int(t[n // 3]) + 137, 0.0005, 100000)):
+        t_up = t_end; t_low = t_end - 4_000_000
+        inp = tmp_path / "in.bin"; outp = tmp_path / "out.bin"
+        with open(inp, "wb") as f:
+            f.write(struct.pack("<i", n)); f.write(t.tobytes()); f.write(struct.pack("<qdiqqd", t_end, half_slice, pen, t_low, t_up, 1e-3))
+        p = subprocess.run([exe, str(inp), str(outp)], capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout + p.stderr
+        raw = open(outp, "rb").read(); off = 0
+        def arr(dtype=np.int64):
+            nonlocal off
+            m = struct.unpack_from("<i", raw, off)[0]; off += 4
+            a = np.frombuffer(raw, dtype, m, off); off += m * np.dtype(dtype).itemsize
+            return a
+        close, sgm, stamps = arr(), arr(), arr()
+        sl = arr(np.dtype([("count", "<i4"), ("median", "<i8")]))
+        assert np.array_equal(close, ind.select_close_events(t, t_end, half_slice, pen))
+        assert np.array_equal(sgm, ind.select_sgm_events(t, t_end, half_slice, pen))
+        assert np.array_equal(stamps, ind.sample_pose_stamps(t_end, half_slice))
+        w = t[(t >= t_low) & (t < t_up)][:-1]
+        counts, med = ind.event_slicing_for_em(w, t_low, t_up, 1e-3)
+        assert np.array_equal(sl["count"], counts) and np.array_equal(sl["median"], med)
+        assert close.size > 0 and stamps.size > 100 and counts.size >= 3
