@@ -329,9 +329,17 @@ OAPI int esvo_oracle_track_get_negative_ts(esvo_oracle_ctx* c, double* neg, doub
 // Pinning tap (tests/test_indep_pins.py): after esvo_oracle_track_reset, select batch 0 like the first solver iteration
 // and return RegProblemLM::operator()(x) and df(0) for it, with the inputs an independent evaluation needs:
 // pts (3 per point, ref frame), Rt = {R_ row-major (9), t_ (3)}.  fjac is row-major n x 6.  Returns the batch size.
+static int track_eval_batch(esvo_oracle_ctx* c, size_t iteration, const double x[6], double* fvec, double* fjac, double* pts, double* Rt, int cap);
 OAPI int esvo_oracle_op_track_eval(esvo_oracle_ctx* c, const double x[6], double* fvec, double* fjac, double* pts, double* Rt, int cap) {
+  return track_eval_batch(c, 0, x, fvec, fjac, pts, Rt, cap);
+}
+// the same for the batch outer iteration `iteration` works on (RegProblemSolverLM.cpp:158-159), at the solver's CURRENT R_, t_
+OAPI int esvo_oracle_op_track_eval_iter(esvo_oracle_ctx* c, int iteration, const double x[6], double* fvec, double* fjac, double* pts, double* Rt, int cap) {
+  return track_eval_batch(c, (size_t)(iteration < 0 ? 0 : iteration), x, fvec, fjac, pts, Rt, cap);
+}
+static int track_eval_batch(esvo_oracle_ctx* c, size_t iteration, const double x[6], double* fvec, double* fjac, double* pts, double* Rt, int cap) {
   if (!c->reg.obs) return ESVO_ERR_STATE;
-  c->reg.setStochasticSampling(0, (size_t)c->prm.trk_batch_size);
+  c->reg.setStochasticSampling((iteration % c->reg.numBatches) * (size_t)c->prm.trk_batch_size, (size_t)c->prm.trk_batch_size);
   const int n = (int)c->reg.numPoints;
   if (n > cap) return ESVO_ERR_CAPACITY;
   std::vector<double> xv(x, x + 6), fv((size_t)n), J;

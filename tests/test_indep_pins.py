@@ -457,44 +457,53 @@ def test_tracking_residual_and_jacobian_vs_numpy(frame):
     assert (fvec != 255).mean() > 0.5
 
 
-def test_tracking_outer_iteration_is_a_minpack_lm_step(frame, oracle_lib):
-    """a19: one pass of RegProblemSolverLM::solve_analytical's loop (RegProblemSolverLM.cpp:150-171) -- batch sampling, x = 0,
-    minimizeInit + ONE minimizeOneStep, addMotionUpdate (RegProblemLM.cpp:349-360), setPose (:362-368) -- checked through what
-    MINPACK's lmder specifies for the first step from x = 0 rather than through a second restatement of lmpar: the step x recovered
-    from the oracle's pose must solve (J^T J + par D^2) x = -J^T f for ONE par >= 0 (D = column norms of J), lie on the initial
-    trust region ||D x|| = delta = factor = 100 within lmpar's 10 % when par > 0, and pass the ratio test.  J and f come from the
-    tap that tests/indep_numpy.py pins; the Cayley / pose algebra is inverted in numpy."""
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_tracking_outer_iteration_is_a_minpack_lm_step(frame, oracle_lib, k):
+    """a19: the k-th pass of RegProblemSolverLM::solve_analytical's loop (RegProblemSolverLM.cpp:150-171) -- batch k-1 of the
+    shuffled cloud, x = 0, minimizeInit + ONE minimizeOneStep, addMotionUpdate (RegProblemLM.cpp:349-360), setPose (:362-368) --
+    checked through what MINPACK's lmder specifies for a first step from x = 0 rather than through a second restatement of lmpar:
+    the step x recovered from the pose after k passes (relative to the state after k-1) must solve (J^T J + par D^2) x = -J^T f
+    for ONE par >= 0 (D = column norms of J), lie on the initial trust region ||D x|| = delta = factor = 100 within lmpar's 10 %
+    when par > 0, and pass the ratio test.  J and f come from the tap that tests/indep_numpy.py pins; the Cayley / pose algebra
+    is inverted in numpy."""
     f = frame
     s = f["s"]
     l, r = configs.rig_calibs(RIG)
-    prm = configs.params_for(RIG, oracle_lib)
-    prm.trk_max_iteration = 1
-    o = capi.Backend(oracle_lib, l, r, prm)
     tl, tr = f["tl"], f["tr"]
-    o.set_ts_pair(tl, tr, s["T_world_left"])
-    sd = s["seeds"]
-    o.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
-    m = o.map_download()
     Tw = np.asarray(s["T_world_left"], float)
-    cloud = (m["p_cam"] @ Tw[:3, :3].T + Tw[:3, 3]).astype(np.float32)
     Tc = Tw.copy(); Tc[:3, 3] += [0.002, 0.001, -0.0015]
-    fn = o.L.lib.esvo_oracle_op_track_eval
-    fn.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 5 + [C.c_int]
-    fn.restype = C.c_int
+    sd = s["seeds"]
     P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+
+    def solver(max_iter):
+        prm = configs.params_for(RIG, oracle_lib)
+        prm.trk_max_iteration = max_iter
+        o = capi.Backend(oracle_lib, l, r, prm)
+        o.set_ts_pair(tl, tr, s["T_world_left"])
+        o.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+        m = o.map_download()
+        cloud = (m["p_cam"] @ Tw[:3, :3].T + Tw[:3, 3]).astype(np.float32)
+        o.track_srand(1)
+        assert o.track_reset(cloud.copy(), Tw, Tc, tl) == 0
+        return o, prm
+    # state after k-1 passes, and the residual / Jacobian of the batch pass k works on, at that state
+    oa, prm = solver(max(k - 1, 1))
+    if k > 1:
+        _, st0 = oa.track_solve(True)
+        assert st0["n_iter"] == k - 1
+    fn = oa.L.lib.esvo_oracle_op_track_eval_iter
+    fn.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_double)] * 5 + [C.c_int]
+    fn.restype = C.c_int
     cap = prm.trk_batch_size
-    _, _, _, mask = o.get_rectify_tables(0)
-    o.track_srand(1)
-    assert o.track_reset(cloud.copy(), Tw, Tc, tl) == 0
-    neg, du, dv = o.track_get_negative_ts()
+    _, _, _, mask = oa.get_rectify_tables(0)
+    neg, du, dv = oa.track_get_negative_ts()
     fvec = np.zeros(cap); fjac = np.zeros((cap, 6)); pts = np.zeros((cap, 3)); Rt = np.zeros(12)
-    assert fn(o.ctx, P(np.zeros(6)), P(fvec), P(fjac), P(pts), P(Rt), cap) == cap
+    assert fn(oa.ctx, k - 1, P(np.zeros(6)), P(fvec), P(fjac), P(pts), P(Rt), cap) == cap
     R_, t_ = Rt[:9].reshape(3, 3).copy(), Rt[9:].copy()
-    # the solver itself, one iteration, same batch (same rand() stream)
-    o.track_srand(1)
-    assert o.track_reset(cloud.copy(), Tw, Tc, tl) == 0
-    T, st = o.track_solve(True)
-    assert st["n_iter"] == 1 and st["nfev"] >= 2
+    # the solver itself, k passes, same rand() stream
+    ob, _ = solver(k)
+    T, st = ob.track_solve(True)
+    assert st["n_iter"] == k and st["nfev"] >= 2 * k
     # invert setPose and addMotionUpdate: R_new = Rw^T R(T), t_new = Rw^T (t(T) - tw); dR = R_new R_^T; Gibbs vector of dR; dt
     R_new = Tw[:3, :3].T @ T[:3, :3]
     t_new = Tw[:3, :3].T @ (T[:3, 3] - Tw[:3, 3])
@@ -504,28 +513,31 @@ def test_tracking_outer_iteration_is_a_minpack_lm_step(frame, oracle_lib):
     c = np.array([A[2, 1], A[0, 2], A[1, 0]])
     assert np.abs(ind.cayley2rot(c) - dR).max() < 1e-12
     x = np.concatenate([c, t_new - dR @ t_])
-    assert np.linalg.norm(x) > 1e-6
+    if np.linalg.norm(x) < 1e-12:
+        # no trial of this pass was accepted: with x = 0 the small-step tests (xtol * ||D x||) cannot fire, lmder leaves through
+        # its ftol test (status 1) and the outer loop goes on with the next batch -- nothing to check about a step
+        pytest.skip("pass %d made no step on this batch" % k)
     # (i) a Levenberg-Marquardt step: J^T J x + J^T f = -par D^2 x for one par >= 0
     D = np.linalg.norm(fjac, axis=0); D[D == 0] = 1.0
     lhs = fjac.T @ (fjac @ x) + fjac.T @ fvec
     d2x = D * D * x
     par = -float(lhs @ d2x) / float(d2x @ d2x)
     assert par >= -1e-12
-    assert np.linalg.norm(lhs + par * d2x) <= 1e-7 * np.linalg.norm(fjac.T @ fvec), (par, np.linalg.norm(lhs + par * d2x))
-    # (ii) on the trust region of the first iteration (delta = factor * ||D x0|| = 0 -> factor), unless the Gauss-Newton step is inside it
+    assert np.linalg.norm(lhs + par * d2x) <= 1e-6 * np.linalg.norm(fjac.T @ fvec), (k, par, np.linalg.norm(lhs + par * d2x))
+    # (ii) on the trust region of a first iteration (delta = factor * ||D x0|| = 0 -> factor), unless the Gauss-Newton step is inside it
     dxn = np.linalg.norm(D * x)
     gn = np.linalg.lstsq(fjac, -fvec, rcond=None)[0]
     if np.linalg.norm(D * gn) <= 1.1 * 100.0:
         assert par < 1e-9 and np.abs(x - gn).max() < 1e-9
     else:
-        assert par > 0 and 0.9 * 100.0 <= dxn <= 1.1 * 100.0, (par, dxn)
+        assert par > 0 and 0.9 * 100.0 <= dxn <= 1.1 * 100.0, (k, par, dxn)
     # (iii) the accepted trial passes the ratio test of lmder (actred / prered >= 1e-4)
     f1 = ind.track_residuals(x, pts, R_, t_, f["Pl"], mask, neg, prm.trk_huber_threshold)
     fn0, fn1 = np.linalg.norm(fvec), np.linalg.norm(f1)
     actred = 1 - (fn1 / fn0) ** 2 if 0.1 * fn1 < fn0 else -1.0
     prered = (np.linalg.norm(fjac @ x) / fn0) ** 2 + 2 * par * (dxn / fn0) ** 2
-    assert prered > 0 and actred / prered >= 1e-4, (actred, prered)
-    print("tracking LM step: par %.3g, ||D x|| %.2f, actred %.3g, prered %.3g, nfev %d" % (par, dxn, actred, prered, st["nfev"]))
+    assert prered > 0 and actred / prered >= 1e-4, (k, actred, prered)
+    print("tracking LM step %d: par %.3g, ||D x|| %.2f, actred %.3g, prered %.3g, nfev %d" % (k, par, dxn, actred, prered, st["nfev"]))
 
 
 def test_cayley_and_J_G_kats():
