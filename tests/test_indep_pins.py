@@ -171,6 +171,53 @@ def test_mapping_at_time_window_bookkeeping_vs_python(oracle_lib, strategy):
         assert max(sizes) < 5 and sizes[-1] <= sizes[-2] + 1 and any(sizes[i + 1] <= sizes[i] for i in range(len(sizes) - 1)), sizes
 
 
+def test_regularisation_keying_deviation_is_small(oracle_lib):
+    """How much of a natural fused map the one documented control-flow deviation touches (DESIGN.md deviation 7): elements whose
+    coordinates a fusion replacement copied from another pixel.  Six consecutive frames through the oracle, the last frame's window
+    replayed by tests/indep_fusion.py: the replayed fusion count equals the oracle's, and the literal reading of
+    DepthRegularization::apply (keyed by the named coordinates) merges well under 1 % of the elements that the true-cell keying
+    of oracle and kernels keeps."""
+    import indep_fusion as inf
+    l, r = configs.rig_calibs(RIG)
+    prm = configs.params_for(RIG, oracle_lib)
+    o = capi.Backend(oracle_lib, l, r, prm)
+    oracle_lib.lib.esvo_oracle_set_irls_shortcut(1)
+    try:
+        for t_ts in (0.50, 0.52, 0.54, 0.56, 0.58, 0.60):
+            s = scenario(RIG, seed=2, n_seeds=1500, t_ts=t_ts)
+            tl, tr = build_ts_pair(o, s); o.ts_reset(0); o.ts_reset(1)
+            o.set_ts_pair(tl, tr, s["T_world_left"])
+            sd = s["seeds"]
+            c = o.mapping_at_time(sd["x"], sd["y"], sd["t"], s["pose_t"], s["poses"])
+    finally:
+        oracle_lib.lib.esvo_oracle_set_irls_shortcut(0)
+    vecs = []
+    while True:
+        try:
+            vecs.append(o.window_download(len(vecs)))
+        except capi.EsvoError:
+            break
+    assert len(vecs) == 6
+    Pl = configs.rig_arrays(RIG)["left"]["P"]
+    grid = inf.Grid(o.H, o.W)
+    nf = 0
+    for v in reversed(vecs):
+        vec = [dict(p_cam=q["p_cam"], s2=float(q["scale2"]), nu=float(q["nu"]), res=float(q["residual"]), age=int(q["age"]),
+                    T_world_cam=q["T_world_cam"]) for q in v]
+        nf += inf.fuse_vector(grid, vec, s["T_world_left"], Pl, o.W, o.H, prm.fusion_radius)
+    assert nf == c["n_fusions"]
+    n_all = len(grid.elements)
+    moved_all = sum(1 for k, e in grid.cell.items() if (e.row, e.col) != k)
+    grid.clean(prm.stdvar_vis_threshold ** 2, prm.age_vis_threshold, prm.invdepth_max_range, prm.invdepth_min_range)
+    moved = sum(1 for k, e in grid.cell.items() if (e.row, e.col) != k)
+    g_true = inf.regularize(grid, prm.reg_radius, prm.reg_min_neighbours, prm.reg_min_close_neighbours, literal=False)
+    g_lit = inf.regularize(grid, prm.reg_radius, prm.reg_min_neighbours, prm.reg_min_close_neighbours, literal=True)
+    merged = len(g_true.elements) - len(g_lit.elements)
+    print("fused map %d elements (%d with copied coordinates); after clean %d (%d); literal regularisation merges %d"
+          % (n_all, moved_all, len(grid.elements), moved, merged))
+    assert 0 <= merged <= moved and merged < 0.01 * len(grid.elements)
+
+
 def _T_left_virtual(f, sd):
     T_left_world = np.linalg.inv(np.asarray(f["s"]["T_world_left"], float))
     return T_left_world @ sd["T_world_virtual"].reshape(4, 4)
